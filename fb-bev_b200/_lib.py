@@ -1,0 +1,120 @@
+"""ctypes binding of ``libfbbev_b200.so`` (C ABI: ``include/fbbev_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel on
+the hot path is in the shared library.  There is NO fallback -- if the library
+is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfbbev_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_p = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/fbbev_b200.h declaration order
+_SIGNATURES = {
+    "fbbev_abi_version": (ctypes.c_int, []),
+    "fbbev_debug_launch_count": (ctypes.c_longlong, []),
+    "fbbev_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "fbbev_bev_pool_v2_fwd": (ctypes.c_int, [_p] * 7 + [_i32, _i32, _p, _p]),
+    "fbbev_bev_pool_v2_dense_workspace_bytes": (_sz, [_i32, _i64]),
+    "fbbev_bev_pool_v2_fwd_dense": (
+        ctypes.c_int, [_p] * 7 + [_i32, _p, _i32, _i32, _i64, _p, _p, _sz, _p]),
+    "fbbev_bev_pool_v2_plan": (
+        ctypes.c_int, [_p, _p, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
+    "fbbev_bev_pool_v2_fwd_dense_planned": (
+        ctypes.c_int, [_p] * 7 + [_i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
+    "fbbev_bev_pool_v2_bwd": (ctypes.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p]),
+    "fbbev_bev_pool_v2_bwd_bczyx": (
+        ctypes.c_int, [_p] * 8 + [_i32, _i32, _i64, _p, _p, _p]),
+    "fbbev_voxel_prepare_workspace_bytes": (_sz, [_i64, _i64]),
+    "fbbev_voxel_prepare": (
+        ctypes.c_int, [_p] + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+    "fbbev_msda_fwd": (ctypes.c_int, [_p] * 5 + [_i32] * 7 + [_p, _p]),
+    "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
+    "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p, _p]),
+    "fbbev_da_sca_fwd": (ctypes.c_int, [_p] * 10 + [_i32] * 10 + [_p, _p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class FbbevError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libfbbev_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1))]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise FbbevError("building libfbbev_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load the library (never builds implicitly; never falls back)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FbbevError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ "
+                f"as g; g.build()'` (or `make -C {CSRC_DIR}`).  The CUDA "
+                "library is the product; there is no CPU or eager fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if _lib.fbbev_abi_version() != 1:
+            raise FbbevError("libfbbev_b200.so ABI version mismatch")
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().fbbev_error_string(code).decode()
+        raise FbbevError(f"{what} failed: {msg} (code {code})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise FbbevError(
+                "fb-bev_b200 ops run on CUDA tensors only (no CPU fallback); "
+                f"got a tensor on {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise FbbevError("all tensors must be on the same CUDA device")
+    return dev
+
+
+def c_floats(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])

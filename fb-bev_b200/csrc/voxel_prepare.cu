@@ -1,0 +1,311 @@
+// voxel_prepare.cu -- device implementation of voxel_pooling_prepare_v2.
+//
+// Replaces  mmdet3d/models/fbbev/view_transformation/forward_projection/
+//           view_transformer.py:547-605
+// (about 25 eager PyTorch ops, a radix sort of ~2e5 keys, three boolean-mask
+// compactions and three host synchronisations per forward) with a counting
+// sort over voxel ranks that never leaves the device:
+//
+//   K1 voxelize   rank[p] = voxel rank of point p or -1; hist[rank]++      (:570-589)
+//   K2 scan       offset[v] = exclusive prefix of hist; interval list =
+//                 occupied voxels in rank order                             (:594-602)
+//   K3 scatter    bucket[offset[r] + atomic slot] = p                       (:590-592)
+//   K4 order      inside each voxel, place points in ascending point index
+//                 (deterministic; == a stable argsort) and emit ranks_bev /
+//                 ranks_depth / ranks_feat                                  (:561-568, :603-605)
+//
+// Integer-path parity rules:
+//   * voxelisation is fp32 subtract, fp32 IEEE divide, truncation toward zero
+//     (`.long()`), so coordinates in (-1, 0) land in cell 0 and are kept;
+//   * the bounds test compares the integer coordinate, converted to float32,
+//     against the FLOAT32 grid size;
+//   * the rank is formed in exact integer arithmetic (the reference's float32
+//     arithmetic is identical below 2^24 voxels and wrong above).
+#include "common.cuh"
+
+namespace fbbev {
+
+constexpr int kPrepThreads = 256;
+constexpr int kScanItems = 8;                       // per thread
+constexpr int kScanTile = kPrepThreads * kScanItems;  // per block
+
+struct GridParams {
+  float lo[3], iv[3], gs[3];
+  int gx, gy, gz;
+};
+
+// `.long()` of the CUDA device the reference runs on: cvt.rzi.s64.f32
+__device__ __forceinline__ long long trunc_i64(float f) {
+  return static_cast<long long>(f);
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_voxelize_kernel(
+    const float* __restrict__ coor, int64_t n_pts, int64_t per_b, GridParams g,
+    int* __restrict__ rank, int* __restrict__ hist) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  const float x = __ldg(coor + 3 * p + 0);
+  const float y = __ldg(coor + 3 * p + 1);
+  const float z = __ldg(coor + 3 * p + 2);
+  // __fsub_rn / __fdiv_rn: IEEE round-to-nearest, never contracted or
+  // replaced by a reciprocal multiply
+  const long long cx = trunc_i64(__fdiv_rn(__fsub_rn(x, g.lo[0]), g.iv[0]));
+  const long long cy = trunc_i64(__fdiv_rn(__fsub_rn(y, g.lo[1]), g.iv[1]));
+  const long long cz = trunc_i64(__fdiv_rn(__fsub_rn(z, g.lo[2]), g.iv[2]));
+  const bool keep = cx >= 0 && (float)cx < g.gs[0] && cy >= 0 &&
+                    (float)cy < g.gs[1] && cz >= 0 && (float)cz < g.gs[2] &&
+                    cx < g.gx && cy < g.gy && cz < g.gz;
+  int r = -1;
+  if (keep) {
+    const int64_t b = p / per_b;
+    r = (int)(((b * g.gz + cz) * g.gy + cy) * g.gx + cx);
+    atomicAdd(hist + r, 1);
+  }
+  rank[p] = r;
+}
+
+// ----- two-quantity exclusive scan over hist: (points, occupied voxels) -----
+__device__ __forceinline__ int2 warp_incl_scan(int2 v, int lane) {
+#pragma unroll
+  for (int o = 1; o < kWarp; o <<= 1) {
+    const int a = __shfl_up_sync(kFull, v.x, o);
+    const int b = __shfl_up_sync(kFull, v.y, o);
+    if (lane >= o) {
+      v.x += a;
+      v.y += b;
+    }
+  }
+  return v;
+}
+
+// inclusive block scan of one int2 per thread; returns block total
+__device__ __forceinline__ int2 block_incl_scan(int2& v, int2* wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_incl_scan(v, lane);
+  if (lane == 31) wsum[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int2 w = lane < kPrepThreads / kWarp ? wsum[lane] : make_int2(0, 0);
+    w = warp_incl_scan(w, lane);
+    if (lane < kPrepThreads / kWarp) wsum[lane] = w;
+  }
+  __syncthreads();
+  if (warp > 0) {
+    v.x += wsum[warp - 1].x;
+    v.y += wsum[warp - 1].y;
+  }
+  const int2 total = wsum[kPrepThreads / kWarp - 1];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_scan_reduce_kernel(
+    const int* __restrict__ hist, int64_t n_vox, int2* __restrict__ block_sums) {
+  __shared__ int2 wsum[kPrepThreads / kWarp];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int2 v = make_int2(0, 0);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + (int64_t)k * kPrepThreads + threadIdx.x;
+    if (i < n_vox) {
+      const int h = hist[i];
+      v.x += h;
+      v.y += h > 0;
+    }
+  }
+  const int2 total = block_incl_scan(v, wsum);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place; totals -> counts
+__global__ void __launch_bounds__(kPrepThreads) prep_scan_spine_kernel(
+    int2* __restrict__ block_sums, int n_blocks, int* __restrict__ counts) {
+  __shared__ int2 wsum[kPrepThreads / kWarp];
+  int2 carry = make_int2(0, 0);
+  for (int base = 0; base < n_blocks; base += kPrepThreads) {
+    const int i = base + threadIdx.x;
+    const int2 mine = i < n_blocks ? block_sums[i] : make_int2(0, 0);
+    int2 v = mine;
+    const int2 total = block_incl_scan(v, wsum);
+    if (i < n_blocks)
+      block_sums[i] = make_int2(carry.x + v.x - mine.x, carry.y + v.y - mine.y);
+    carry.x += total.x;
+    carry.y += total.y;
+  }
+  if (threadIdx.x == 0) {
+    counts[0] = carry.x;  // n_kept
+    counts[1] = carry.y;  // n_intervals
+  }
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_scan_apply_kernel(
+    const int* __restrict__ hist, int64_t n_vox,
+    const int2* __restrict__ block_sums, int* __restrict__ offset,
+    int* __restrict__ interval_starts, int* __restrict__ interval_lengths) {
+  __shared__ int2 wsum[kPrepThreads / kWarp];
+  // blocked arrangement: thread t owns kScanItems consecutive voxels
+  const int64_t base =
+      (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int h[kScanItems];
+  int2 v = make_int2(0, 0);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    h[k] = i < n_vox ? hist[i] : 0;
+    v.x += h[k];
+    v.y += h[k] > 0;
+  }
+  const int2 mine = v;
+  block_incl_scan(v, wsum);
+  const int2 bs = block_sums[blockIdx.x];
+  int run_pts = bs.x + v.x - mine.x;  // exclusive prefix for this thread
+  int run_int = bs.y + v.y - mine.y;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    if (i < n_vox) {
+      offset[i] = run_pts;
+      if (h[k] > 0) {
+        interval_starts[run_int] = run_pts;   // view_transformer.py:597
+        interval_lengths[run_int] = h[k];     // :599-602
+        run_int++;
+      }
+      run_pts += h[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_scatter_kernel(
+    const int* __restrict__ rank, int64_t n_pts, const int* __restrict__ offset,
+    int* __restrict__ cursor, int* __restrict__ bucket) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  const int r = rank[p];
+  if (r < 0) return;
+  const int s = atomicAdd(cursor + r, 1);
+  bucket[offset[r] + s] = (int)p;
+}
+
+// One thread per kept point: its final position inside its voxel's run is the
+// number of bucket mates with a smaller point index.
+__global__ void __launch_bounds__(kPrepThreads) prep_order_kernel(
+    const int* __restrict__ bucket, const int* __restrict__ rank,
+    const int* __restrict__ offset, const int* __restrict__ hist,
+    const int* __restrict__ counts, int D, int64_t hw,
+    int* __restrict__ ranks_bev, int* __restrict__ ranks_depth,
+    int* __restrict__ ranks_feat) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= counts[0]) return;
+  const int p = bucket[j];
+  const int r = rank[p];
+  const int s = offset[r];
+  const int len = hist[r];
+  int pos = 0;
+  for (int k = 0; k < len; ++k) pos += bucket[s + k] < p;
+  const int dst = s + pos;
+  ranks_bev[dst] = r;
+  ranks_depth[dst] = p;  // arange(num_points), view_transformer.py:561-562
+  // arange(num_points // D).reshape(B,N,1,H,W).expand(B,N,D,H,W), :563-568
+  const int64_t bn = p / ((int64_t)D * hw);
+  ranks_feat[dst] = (int)(bn * hw + p % hw);
+}
+
+struct PrepWorkspace {
+  int* rank;      // [n_pts]
+  int* bucket;    // [n_pts]
+  int* hist;      // [n_vox]
+  int* cursor;    // [n_vox]   (hist and cursor are contiguous: one memset)
+  int* offset;    // [n_vox]
+  int2* block_sums;  // [n_scan_blocks]
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t prep_layout(int64_t n_pts, int64_t n_vox, char* base,
+                          PrepWorkspace* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t n_scan_blocks = ceil_div64(n_vox, kScanTile);
+  char* rank = take((size_t)n_pts * 4);
+  char* bucket = take((size_t)n_pts * 4);
+  char* hist = take((size_t)n_vox * 2 * 4);  // hist | cursor
+  char* offset = take((size_t)n_vox * 4);
+  char* bsum = take((size_t)n_scan_blocks * sizeof(int2));
+  if (w) {
+    w->rank = reinterpret_cast<int*>(rank);
+    w->bucket = reinterpret_cast<int*>(bucket);
+    w->hist = reinterpret_cast<int*>(hist);
+    w->cursor = w->hist + n_vox;
+    w->offset = reinterpret_cast<int*>(offset);
+    w->block_sums = reinterpret_cast<int2*>(bsum);
+  }
+  return off;
+}
+
+}  // namespace fbbev
+
+using namespace fbbev;
+
+FBBEV_API size_t fbbev_voxel_prepare_workspace_bytes(int64_t n_points,
+                                                     int64_t n_voxels_total) {
+  if (n_points <= 0 || n_voxels_total <= 0) return 0;
+  return prep_layout(n_points, n_voxels_total, nullptr, nullptr);
+}
+
+FBBEV_API int fbbev_voxel_prepare(
+    const float* coor, int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+    const float* lo_host, const float* iv_host, const float* gs_host,
+    int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+    int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts,
+    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
+  if (B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || !lo_host || !iv_host ||
+      !gs_host)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (!coor || !ranks_bev || !ranks_depth || !ranks_feat || !interval_starts ||
+      !interval_lengths || !counts || !workspace)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  GridParams g;
+  for (int k = 0; k < 3; ++k) {
+    g.lo[k] = lo_host[k];
+    g.iv[k] = iv_host[k];
+    g.gs[k] = gs_host[k];
+    if (!(gs_host[k] >= 1.f) || gs_host[k] > 1e9f)
+      return FBBEV_ERR_INVALID_ARGUMENT;
+  }
+  g.gx = (int)gs_host[0];  // int(self.grid_size[i]), view_transformer.py:537-538
+  g.gy = (int)gs_host[1];
+  g.gz = (int)gs_host[2];
+  const int64_t n_pts = (int64_t)B * N * D * H * W;
+  const int64_t n_vox = (int64_t)B * g.gx * g.gy * g.gz;
+  if (n_pts > INT32_MAX || n_vox > INT32_MAX) return FBBEV_ERR_UNSUPPORTED;
+  PrepWorkspace w;
+  const size_t need =
+      prep_layout(n_pts, n_vox, static_cast<char*>(workspace), &w);
+  if (workspace_bytes < need) return FBBEV_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t st = as_stream(stream);
+
+  cudaError_t e = cudaMemsetAsync(w.hist, 0, (size_t)n_vox * 2 * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  const unsigned pt_grid = (unsigned)ceil_div64(n_pts, kPrepThreads);
+  const int n_scan_blocks = (int)ceil_div64(n_vox, kScanTile);
+  count_launch(6);
+  prep_voxelize_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
+      coor, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
+  prep_scan_reduce_kernel<<<n_scan_blocks, kPrepThreads, 0, st>>>(
+      w.hist, n_vox, w.block_sums);
+  prep_scan_spine_kernel<<<1, kPrepThreads, 0, st>>>(w.block_sums,
+                                                     n_scan_blocks, counts);
+  prep_scan_apply_kernel<<<n_scan_blocks, kPrepThreads, 0, st>>>(
+      w.hist, n_vox, w.block_sums, w.offset, interval_starts,
+      interval_lengths);
+  prep_scatter_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
+      w.rank, n_pts, w.offset, w.cursor, w.bucket);
+  prep_order_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
+      w.bucket, w.rank, w.offset, w.hist, counts, D, (int64_t)H * W, ranks_bev,
+      ranks_depth, ranks_feat);
+  return launch_status();
+}

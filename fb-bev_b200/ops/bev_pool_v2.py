@@ -1,0 +1,258 @@
+"""``bev_pool_v2`` -- host-side mirror of the reference operator.
+
+Mirrors ``mmdet3d/ops/bev_pool_v2/bev_pool.py`` (names, argument order and
+meaning, output layout):
+
+* ``QuickCumsumCuda``   -- bev_pool.py:12-81: autograd function over the
+  reference-layout kernels; ``forward`` returns ``(B, Z, Y, X, C)``.
+* ``bev_pool_v2()``     -- bev_pool.py:84-90: returns the contiguous
+  ``(B, C, Z, Y, X)`` tensor.  Here it is ONE fused kernel
+  (``fbbev_bev_pool_v2_fwd_dense``) instead of memset + kernel + transpose copy.
+* ``voxel_pooling_prepare_v2`` -- device implementation of
+  view_transformer.py:547-605 (``fbbev_voxel_prepare``).
+
+All compute is in ``libfbbev_b200.so``; tensors must be CUDA tensors.
+"""
+import torch
+
+from .. import _lib
+
+__all__ = ['bev_pool_v2', 'bev_pool_v2_dense', 'QuickCumsumCuda',
+           'voxel_pooling_prepare_v2', 'VoxelIndex']
+
+
+def _feat_intervals(ranks_feat, ranks_depth, ranks_bev):
+    """Re-sort the point list by feature pixel and rebuild intervals --
+    QuickCumsumCuda.backward, bev_pool.py:45-55 (torch ops; plumbing)."""
+    order = torch.sort(ranks_feat, stable=True)[1]
+    ranks_feat, ranks_depth, ranks_bev = \
+        ranks_feat[order], ranks_depth[order], ranks_bev[order]
+    kept = torch.ones(ranks_bev.shape[0], device=ranks_bev.device,
+                      dtype=torch.bool)
+    kept[1:] = ranks_feat[1:] != ranks_feat[:-1]
+    interval_starts_bp = torch.where(kept)[0].int()
+    interval_lengths_bp = torch.zeros_like(interval_starts_bp)
+    interval_lengths_bp[:-1] = interval_starts_bp[1:] - interval_starts_bp[:-1]
+    interval_lengths_bp[-1] = ranks_bev.shape[0] - interval_starts_bp[-1]
+    return (ranks_feat.contiguous(), ranks_depth.contiguous(),
+            ranks_bev.contiguous(), interval_starts_bp.contiguous(),
+            interval_lengths_bp.contiguous())
+
+
+class QuickCumsumCuda(torch.autograd.Function):
+    """Same contract as the reference class (bev_pool.py:12-81)."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths):
+        dev = _lib.require_cuda(depth, feat, ranks_depth, ranks_feat,
+                                ranks_bev, interval_starts, interval_lengths)
+        ranks_bev = ranks_bev.int()
+        depth = depth.contiguous().float()
+        feat = feat.contiguous().float()
+        ranks_depth = ranks_depth.contiguous().int()
+        ranks_feat = ranks_feat.contiguous().int()
+        interval_lengths = interval_lengths.contiguous().int()
+        interval_starts = interval_starts.contiguous().int()
+
+        out = feat.new_zeros(bev_feat_shape)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fbbev_bev_pool_v2_fwd(
+                _lib.ptr(depth), _lib.ptr(feat), _lib.ptr(ranks_depth),
+                _lib.ptr(ranks_feat), _lib.ptr(ranks_bev),
+                _lib.ptr(interval_starts), _lib.ptr(interval_lengths),
+                interval_lengths.shape[0], feat.shape[-1], _lib.ptr(out),
+                _lib.stream_ptr(dev))
+        _lib.check(rc, 'fbbev_bev_pool_v2_fwd')
+        ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        ranks_bev, depth, feat, ranks_feat, ranks_depth = ctx.saved_tensors
+        dev = depth.device
+        ranks_feat, ranks_depth, ranks_bev, starts_bp, lengths_bp = \
+            _feat_intervals(ranks_feat, ranks_depth, ranks_bev)
+        depth_grad = depth.new_zeros(depth.shape)
+        feat_grad = feat.new_zeros(feat.shape)
+        out_grad = out_grad.contiguous().float()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fbbev_bev_pool_v2_bwd(
+                _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(feat),
+                _lib.ptr(ranks_depth), _lib.ptr(ranks_feat),
+                _lib.ptr(ranks_bev), _lib.ptr(starts_bp), _lib.ptr(lengths_bp),
+                lengths_bp.shape[0], feat.shape[-1], _lib.ptr(depth_grad),
+                _lib.ptr(feat_grad), _lib.stream_ptr(dev))
+        _lib.check(rc, 'fbbev_bev_pool_v2_bwd')
+        return depth_grad, feat_grad, None, None, None, None, None, None
+
+
+def _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                   bev_feat_shape, interval_starts, interval_lengths,
+                   n_intervals_dev):
+    dev = _lib.require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                            interval_starts, interval_lengths, n_intervals_dev)
+    B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
+    assert feat.shape[-1] == C, (feat.shape, bev_feat_shape)
+    L = _lib.lib()
+    out = torch.empty((B, C, Z, Y, X), dtype=torch.float32, device=dev)
+    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, Z * Y * X)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.fbbev_bev_pool_v2_fwd_dense(
+            _lib.ptr(depth), _lib.ptr(feat), _lib.ptr(ranks_depth),
+            _lib.ptr(ranks_feat), _lib.ptr(ranks_bev),
+            _lib.ptr(interval_starts), _lib.ptr(interval_lengths),
+            interval_lengths.shape[0], _lib.ptr(n_intervals_dev), C, B,
+            Z * Y * X, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+            _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_bev_pool_v2_fwd_dense')
+    return out
+
+
+class _BevPoolV2Dense(torch.autograd.Function):
+    """Fused op: (B,C,Z,Y,X) out, gradient consumed in that layout."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths,
+                n_intervals_dev, n_kept_dev):
+        ranks_bev = ranks_bev.contiguous().int()
+        depth = depth.contiguous().float()
+        feat = feat.contiguous().float()
+        ranks_depth = ranks_depth.contiguous().int()
+        ranks_feat = ranks_feat.contiguous().int()
+        interval_lengths = interval_lengths.contiguous().int()
+        interval_starts = interval_starts.contiguous().int()
+        out = _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                             bev_feat_shape, interval_starts, interval_lengths,
+                             n_intervals_dev)
+        ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth,
+                              n_kept_dev)
+        ctx.has_count = n_kept_dev is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        ranks_bev, depth, feat, ranks_feat, ranks_depth, n_kept_dev = \
+            ctx.saved_tensors
+        dev = depth.device
+        if n_kept_dev is not None:
+            # padded index buffers from the sync-free path: trim (one sync,
+            # backward only)
+            n = int(n_kept_dev.item())
+            ranks_bev, ranks_feat, ranks_depth = \
+                ranks_bev[:n], ranks_feat[:n], ranks_depth[:n]
+        depth_grad = depth.new_zeros(depth.shape)
+        feat_grad = feat.new_zeros(feat.shape)
+        if ranks_bev.shape[0] > 0:
+            ranks_feat, ranks_depth, ranks_bev, starts_bp, lengths_bp = \
+                _feat_intervals(ranks_feat, ranks_depth, ranks_bev)
+            out_grad = out_grad.contiguous().float()  # (B,C,Z,Y,X)
+            B, C, Z, Y, X = out_grad.shape
+            with torch.cuda.device(dev):
+                rc = _lib.lib().fbbev_bev_pool_v2_bwd_bczyx(
+                    _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(feat),
+                    _lib.ptr(ranks_depth), _lib.ptr(ranks_feat),
+                    _lib.ptr(ranks_bev), _lib.ptr(starts_bp),
+                    _lib.ptr(lengths_bp), lengths_bp.shape[0], C, Z * Y * X,
+                    _lib.ptr(depth_grad), _lib.ptr(feat_grad),
+                    _lib.stream_ptr(dev))
+            _lib.check(rc, 'fbbev_bev_pool_v2_bwd_bczyx')
+        return (depth_grad, feat_grad) + (None,) * 8
+
+
+def bev_pool_v2_dense(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                      bev_feat_shape, interval_starts, interval_lengths,
+                      n_intervals_dev=None, n_kept_dev=None):
+    """Fused ``bev_pool_v2``: returns contiguous ``(B, C, Z, Y, X)``.
+
+    ``n_intervals_dev`` / ``n_kept_dev`` (0-dim int32 CUDA tensors) mark the
+    live prefix of over-allocated index buffers, as produced by
+    :func:`voxel_pooling_prepare_v2` with ``sync=False``.
+    """
+    return _BevPoolV2Dense.apply(depth, feat, ranks_depth, ranks_feat,
+                                 ranks_bev, bev_feat_shape, interval_starts,
+                                 interval_lengths, n_intervals_dev, n_kept_dev)
+
+
+def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths):
+    """Drop-in for the reference ``bev_pool_v2`` (bev_pool.py:84-90).
+
+    depth ``(B,N,D,H,W)``, feat ``(B,N,H,W,C)`` (any strides), int index
+    tensors as returned by ``voxel_pooling_prepare_v2``; ``bev_feat_shape`` =
+    ``(B, Z, Y, X, C)``.  Returns contiguous ``(B, C, Z, Y, X)``.
+    Requires the interval list to be ordered by voxel rank (it always is when
+    it comes from ``voxel_pooling_prepare_v2``); use ``QuickCumsumCuda`` for
+    arbitrary interval lists.
+    """
+    return bev_pool_v2_dense(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                             bev_feat_shape, interval_starts, interval_lengths)
+
+
+class VoxelIndex:
+    """Index tensors of one ``voxel_pooling_prepare_v2`` call, device-resident.
+
+    The five index tensors are over-allocated (``n_points`` entries); the live
+    prefix lengths are ``counts[0]`` (points kept) and ``counts[1]``
+    (intervals), int32 on the device.  Nothing here forces a host sync.
+    """
+
+    def __init__(self, ranks_bev, ranks_depth, ranks_feat, interval_starts,
+                 interval_lengths, counts):
+        self.ranks_bev = ranks_bev
+        self.ranks_depth = ranks_depth
+        self.ranks_feat = ranks_feat
+        self.interval_starts = interval_starts
+        self.interval_lengths = interval_lengths
+        self.counts = counts
+
+    @property
+    def n_kept_dev(self):
+        return self.counts[0]
+
+    @property
+    def n_intervals_dev(self):
+        return self.counts[1]
+
+    def trimmed(self):
+        """Exact-length tensors as the reference returns them (host sync);
+        five ``None`` when nothing is kept (view_transformer.py:598-599)."""
+        n_kept, n_int = (int(v) for v in self.counts.tolist())
+        if n_int == 0:
+            return None, None, None, None, None
+        return (self.ranks_bev[:n_kept], self.ranks_depth[:n_kept],
+                self.ranks_feat[:n_kept], self.interval_starts[:n_int],
+                self.interval_lengths[:n_int])
+
+
+def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
+    """Device ``voxel_pooling_prepare_v2`` (view_transformer.py:547-605).
+
+    coor ``(B,N,D,H,W,3)`` fp32 CUDA; the three grid descriptors are the
+    3-element float32 tensors of ``create_grid_infos`` (:384-387) -- host
+    tensors or python sequences.  Returns a :class:`VoxelIndex`.
+    """
+    dev = _lib.require_cuda(coor)
+    coor = coor.contiguous().float()
+    B, N, D, H, W, three = coor.shape
+    assert three == 3
+    lo = [float(v) for v in torch.as_tensor(grid_lower_bound).float().cpu()]
+    iv = [float(v) for v in torch.as_tensor(grid_interval).float().cpu()]
+    gs = [float(v) for v in torch.as_tensor(grid_size).float().cpu()]
+    n_pts = B * N * D * H * W
+    n_vox = B * int(gs[0]) * int(gs[1]) * int(gs[2])
+    L = _lib.lib()
+    idx = torch.empty((5, n_pts), dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.fbbev_voxel_prepare(
+            _lib.ptr(coor), B, N, D, H, W, _lib.c_floats(lo), _lib.c_floats(iv),
+            _lib.c_floats(gs), _lib.ptr(idx[0]), _lib.ptr(idx[1]),
+            _lib.ptr(idx[2]), _lib.ptr(idx[3]), _lib.ptr(idx[4]),
+            _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_voxel_prepare')
+    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts)

@@ -1,0 +1,4 @@
+"""Plugin classes of the forward-backward view transformation (mirror of
+``mmdet3d/models/fbbev/view_transformation``).  Importing this package
+registers them (see ``registry.py``)."""
+from .forward_projection import *  # noqa: F401,F403

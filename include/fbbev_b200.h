@@ -1,0 +1,258 @@
+/*
+ * fbbev_b200.h -- C ABI of libfbbev_b200.so: the B200 (sm_100a) implementation
+ * of the FB-BEV / FB-OCC forward-backward view-transformation hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in `_host`;
+ *   - the caller owns every buffer including workspaces; nothing is allocated,
+ *     no host<->device synchronisation happens inside a call, and all work is
+ *     enqueued on `stream` (a cudaStream_t; NULL = legacy default stream);
+ *   - return value: 0 on success, a negative FBBEV_ERR_* for argument errors,
+ *     or a positive cudaError_t raised while enqueuing.  Nothing throws.
+ *   - re-entrant per stream; no global mutable state.
+ *
+ * Each entry point names the reference interface it replaces (paths relative
+ * to the NVlabs/FB-BEV checkout).  INTEGRATION.md shows the reference-side
+ * binding for each.
+ */
+#ifndef FBBEV_B200_H_
+#define FBBEV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBBEV_OK 0
+#define FBBEV_ERR_INVALID_ARGUMENT (-1)
+#define FBBEV_ERR_WORKSPACE_TOO_SMALL (-2)
+#define FBBEV_ERR_UNSUPPORTED (-3)
+
+#define FBBEV_ABI_VERSION 1
+
+typedef void* fbbev_stream_t; /* cudaStream_t */
+
+int fbbev_abi_version(void);
+/* Diagnostics: cumulative number of kernel launches issued by this library. */
+long long fbbev_debug_launch_count(void);
+/* Static string for a return code of any entry point. */
+const char* fbbev_error_string(int code);
+
+/* =====================================================================
+ * F -- lift-splat voxel pooling (bev_pool_v2)
+ * ===================================================================== */
+
+/*
+ * Drop-in for `bev_pool_v2_ext.bev_pool_v2_forward`
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:28-55 (launcher
+ *   bev_pool_cuda.cu:120-128, kernel :18-45).
+ * depth (B,N,D,H,W) fp32; feat (B,N,H,W,C) fp32; index arrays int32;
+ * out (B,Z,Y,X,C) fp32, ZERO-FILLED BY THE CALLER as in bev_pool.py:25.
+ * Semantics identical to the reference for arbitrary interval lists: one
+ * plain store of the interval sum to voxel ranks_bev[interval_starts[i]].
+ * Differences: 64-bit offsets (the reference overflows int32 when
+ * B*Z*Y*X*C >= 2^31) and the caller's stream instead of the legacy stream.
+ */
+int fbbev_bev_pool_v2_fwd(const float* depth, const float* feat,
+                          const int32_t* ranks_depth,
+                          const int32_t* ranks_feat, const int32_t* ranks_bev,
+                          const int32_t* interval_starts,
+                          const int32_t* interval_lengths, int32_t n_intervals,
+                          int32_t c, float* out, fbbev_stream_t stream);
+
+/*
+ * Fused replacement for the whole reference op
+ *   `bev_pool_v2()` = QuickCumsumCuda.forward + permute(0,4,1,2,3).contiguous()
+ *   mmdet3d/ops/bev_pool_v2/bev_pool.py:15-39, 84-90.
+ * Writes EVERY element of out exactly once, directly in the op's final
+ * (B,C,Z,Y,X) layout: no caller-side memset, no transpose pass.
+ *
+ * Precondition (what voxel_pooling_prepare_v2 always produces,
+ * view_transformer.py:590-602): intervals are listed in non-decreasing order
+ * of their voxel rank ranks_bev[interval_starts[i]], one interval per voxel.
+ * Out-of-range ranks are ignored (memory-safe).
+ *
+ * n_intervals_dev: optional device int32 holding the live interval count
+ *   (<= n_intervals_max); NULL means n_intervals_max is the count.  This lets
+ *   the prepare -> pool chain run without a host sync / under CUDA graphs.
+ * n_voxels_per_sample = Z*Y*X.  Requires B*Z*Y*X < 2^31 (int32 ranks).
+ * workspace: >= fbbev_bev_pool_v2_dense_workspace_bytes(...) bytes.
+ */
+size_t fbbev_bev_pool_v2_dense_workspace_bytes(int32_t batch,
+                                               int64_t n_voxels_per_sample);
+int fbbev_bev_pool_v2_fwd_dense(
+    const float* depth, const float* feat, const int32_t* ranks_depth,
+    const int32_t* ranks_feat, const int32_t* ranks_bev,
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
+    int32_t batch, int64_t n_voxels_per_sample, float* out, void* workspace,
+    size_t workspace_bytes, fbbev_stream_t stream);
+
+/*
+ * The two halves of fbbev_bev_pool_v2_fwd_dense, for callers that reuse an
+ * index (static camera rig, `accelerate=True`, view_transformer.py:261-283):
+ * `plan` builds the tile table for a given (index, C) once; `_planned` is then
+ * a single kernel launch per forward.
+ */
+int fbbev_bev_pool_v2_plan(const int32_t* ranks_bev,
+                           const int32_t* interval_starts,
+                           int32_t n_intervals_max,
+                           const int32_t* n_intervals_dev, int32_t c,
+                           int32_t batch, int64_t n_voxels_per_sample,
+                           void* workspace, size_t workspace_bytes,
+                           fbbev_stream_t stream);
+int fbbev_bev_pool_v2_fwd_dense_planned(
+    const float* depth, const float* feat, const int32_t* ranks_depth,
+    const int32_t* ranks_feat, const int32_t* ranks_bev,
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, float* out, const void* plan,
+    size_t plan_bytes, fbbev_stream_t stream);
+
+/*
+ * Drop-in for `bev_pool_v2_ext.bev_pool_v2_backward`
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:72-102 (kernel
+ *   bev_pool_cuda.cu:64-118).  Intervals are runs of equal ranks_feat
+ *   (bev_pool.py:45-55).  out_grad (B,Z,Y,X,C); depth_grad / feat_grad
+ *   zero-filled by the caller (bev_pool.py:65-66).
+ */
+int fbbev_bev_pool_v2_bwd(const float* out_grad, const float* depth,
+                          const float* feat, const int32_t* ranks_depth,
+                          const int32_t* ranks_feat, const int32_t* ranks_bev,
+                          const int32_t* interval_starts,
+                          const int32_t* interval_lengths, int32_t n_intervals,
+                          int32_t c, float* depth_grad, float* feat_grad,
+                          fbbev_stream_t stream);
+
+/*
+ * Same contract as fbbev_bev_pool_v2_bwd, but out_grad is (B,C,Z,Y,X) -- the
+ * layout of the tensor `bev_pool_v2()` returns (bev_pool.py:89), i.e. the
+ * gradient as autograd delivers it -- so the full-volume transpose copy the
+ * reference performs first (`out_grad.contiguous()`, bev_pool.py:67) is skipped.
+ */
+int fbbev_bev_pool_v2_bwd_bczyx(
+    const float* out_grad, const float* depth, const float* feat,
+    const int32_t* ranks_depth, const int32_t* ranks_feat,
+    const int32_t* ranks_bev, const int32_t* interval_starts,
+    const int32_t* interval_lengths, int32_t n_intervals, int32_t c,
+    int64_t n_voxels_per_sample, float* depth_grad, float* feat_grad,
+    fbbev_stream_t stream);
+
+/*
+ * Device implementation of `voxel_pooling_prepare_v2`
+ *   mmdet3d/models/fbbev/view_transformation/forward_projection/
+ *   view_transformer.py:547-605  (integer path, bit-exact).
+ * coor (B,N,D,H,W,3) fp32 ego-frame points from get_lidar_coor (:458-498).
+ * lo/iv/gs: grid lower bound, interval and FLOAT32 grid size (:384-387).
+ * Outputs (each sized for B*N*D*H*W entries): ranks_bev / ranks_depth /
+ * ranks_feat sorted by voxel rank, ascending point index inside a voxel
+ * (a stable sort; the reference's argsort order inside a voxel is
+ * unspecified), interval_starts / interval_lengths; counts[0] = n_kept,
+ * counts[1] = n_intervals (device int32[2]).
+ * Voxel rank is computed in exact integer arithmetic; the reference computes
+ * it in float32 (:586-589), which is identical while B*Z*Y*X < 2^24.
+ * Requires B*Z*Y*X < 2^31 and B*N*D*H*W < 2^31.
+ */
+size_t fbbev_voxel_prepare_workspace_bytes(int64_t n_points,
+                                           int64_t n_voxels_total);
+int fbbev_voxel_prepare(const float* coor, int32_t B, int32_t N, int32_t D,
+                        int32_t H, int32_t W, const float* lo_host,
+                        const float* iv_host, const float* gs_host,
+                        int32_t* ranks_bev, int32_t* ranks_depth,
+                        int32_t* ranks_feat, int32_t* interval_starts,
+                        int32_t* interval_lengths, int32_t* counts,
+                        void* workspace, size_t workspace_bytes,
+                        fbbev_stream_t stream);
+
+/* =====================================================================
+ * B -- BEV -> image depth-aware spatial cross-attention (MSDeformAttn)
+ * ===================================================================== */
+
+/*
+ * Drop-in for `ext_module.ms_deform_attn_forward` (mmcv-full 1.5.2 `_ext`)
+ *   call site: .../backward_projection/bevformer_utils/
+ *   multi_scale_deformable_attn_function.py:127-133.
+ * value (bs, n_value, heads, ch) fp32; spatial_shapes (levels,2) and
+ * level_start (levels) are DEVICE int64 as in the reference
+ * (bevformer.py:108-111); loc (bs,nq,heads,levels,points,2) as (x,y) in
+ * [0,1]; attw (bs,nq,heads,levels,points); out (bs,nq,heads*ch).
+ * No im2col_step restriction.
+ */
+int fbbev_msda_fwd(const float* value, const int64_t* spatial_shapes,
+                   const int64_t* level_start, const float* loc,
+                   const float* attw, int32_t bs, int32_t n_value,
+                   int32_t heads, int32_t ch, int32_t levels, int32_t nq,
+                   int32_t points, float* out, fbbev_stream_t stream);
+
+/*
+ * Drop-in for `ext_module.ms_deform_attn_backward`
+ *   call site: multi_scale_deformable_attn_function.py:159-169.
+ * grad_value / grad_loc / grad_attw zero-filled by the caller (:155-157).
+ */
+int fbbev_msda_bwd(const float* value, const int64_t* spatial_shapes,
+                   const int64_t* level_start, const float* loc,
+                   const float* attw, const float* grad_out, int32_t bs,
+                   int32_t n_value, int32_t heads, int32_t ch, int32_t levels,
+                   int32_t nq, int32_t points, float* grad_value,
+                   float* grad_loc, float* grad_attw, fbbev_stream_t stream);
+
+/*
+ * Fused core of mmcv `MultiScaleDeformableAttention.forward` (the encoder
+ * layer's self_attn, fbocc-r50 config :176-180): softmax over levels*points,
+ * sampling_locations = ref + offsets / (W_l, H_l), bilinear sampling and
+ * weighted sum in one kernel -- `loc` / normalised `attw` never touch HBM.
+ * ref (bs,nq,levels,2); offsets (bs,nq,heads,levels,points,2) = raw output of
+ * the sampling_offsets Linear; logits (bs,nq,heads,levels,points) = raw output
+ * of the attention_weights Linear; out (bs,nq,heads*ch).
+ */
+int fbbev_msda_fused_fwd(const float* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start, const float* ref,
+                         const float* offsets, const float* logits, int32_t bs,
+                         int32_t n_value, int32_t heads, int32_t ch,
+                         int32_t levels, int32_t nq, int32_t points,
+                         float* out, fbbev_stream_t stream);
+
+/*
+ * Fused depth-aware spatial cross-attention: everything between the three
+ * input Linears and `output_proj` of
+ *   DA_SpatialCrossAttention.forward   spatial_cross_attention_depth.py:86-223
+ *   DA_MSDeformableAttention.forward   spatial_cross_attention_depth.py:465-601
+ * i.e. per-camera query selection (:156-169), rebatch (:173-186), depth bin
+ * one-hot (:196-199), softmax (:540), sampling locations (:554-570), the depth
+ * look-up MSDA launch (:584-591), depth re-weighting (:592), the main MSDA
+ * launch (:593-595), scatter-add over cameras (:208-211) and the division by
+ * the per-query camera count (:213-216).
+ *
+ * value      (bs*n_cams, n_value, heads, ch)  value_proj(feat), camera-major
+ *            inside a sample (row = b*n_cams + cam), as at :188-191
+ * depth_prob (bs*n_cams, H0*W0, DC)  pred_img_depth flattened as at :131-133
+ * ref_cam    (n_cams, bs, nq, Z, 2)  reference_points_cam (bevformer_encoder.py:117)
+ * ref_depth  (n_cams, bs, nq, Z)     bev_query_depth (:120)
+ * mask       (n_cams, bs, nq, Z) uint8   per_cam_mask_list (:118)
+ * offsets    (bs, nq, heads, levels, points, 2)  raw sampling_offsets(query)
+ * logits     (bs, nq, heads, levels, points)     raw attention_weights(query)
+ *   (both Linears act row-wise, so evaluating them once per BEV query equals
+ *    the reference's evaluation on the re-batched copies)
+ * points = num_points (all Z anchors), Z = num_Z_anchors, point index
+ *   = p*Z + z (:563-570, :590).
+ * dbound_host = (d_min, d_max, d_step) (:196); DC = depth bins.
+ * out        (bs, nq, heads*ch) = slots / clamp(count, 1), the tensor the
+ *            reference feeds to output_proj (:219).
+ * bev_mask (:156-159) is not supported by this entry point (NULL only).
+ */
+int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
+                     const float* ref_cam, const float* ref_depth,
+                     const uint8_t* mask, const float* offsets,
+                     const float* logits, const int64_t* spatial_shapes,
+                     const int64_t* level_start, const float* dbound_host,
+                     int32_t bs, int32_t n_cams, int32_t nq, int32_t n_value,
+                     int32_t heads, int32_t ch, int32_t levels, int32_t points,
+                     int32_t Z, int32_t DC, float* out, fbbev_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBBEV_B200_H_ */

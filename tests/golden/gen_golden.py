@@ -1,0 +1,127 @@
+"""Generate the committed golden fixtures from the reference's OWN Python.
+
+Run in the build container (needs /root/reference):
+
+    python tests/golden/gen_golden.py
+
+It imports the reference's view-transformation modules through
+``tests/golden/ref_import.py`` (mmcv stand-ins, reference files loaded from
+/root/reference, nothing copied) and records small seeded input/output pairs as
+``tests/golden/*.npz``.  The tests read only the ``.npz`` files, so they run on
+the GPU box where the reference checkout does not exist.
+
+What each fixture pins (reference file:line):
+  f_*      get_lidar_coor (view_transformer.py:458-498), voxel_pooling_prepare_v2
+           (:547-605) and voxel_pooling_v2 glue (:521-545) of
+           LSSViewTransformerFunction3D, run on CPU by the reference code itself.
+           The bev_pool_v2 CUDA op inside is served by the C oracle (the
+           reference has no CPU kernel); its own known-answer test
+           (bev_pool.py:145-176) is restated in tests/test_oracle.py.
+  b_*      DA_SpatialCrossAttention / DA_MSDeformableAttention / bevformer
+           encoder / BackwardProjection forward (spatial_cross_attention_depth.py,
+           bevformer_encoder.py, bevformer.py, backward_projection.py), run by
+           the reference code with mmcv's `_ext` MSDA op served by the C oracle.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_import  # noqa: E402
+from fbbev_b200 import synthetic  # noqa: E402
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    arrays = {k: v for k, v in arrays.items() if v is not None}
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def gen_forward(ref):
+    VT = ref.view_transformer.LSSViewTransformerFunction3D
+
+    def run_case(name, grid_config, input_size, downsample, B, N, C, seed,
+                 coor_override=None):
+        vt = VT(grid_config=grid_config, input_size=input_size,
+                downsample=downsample)
+        cam = synthetic.make_cam_params(B, N, input_size=input_size,
+                                        jitter=1.0, seed=seed)
+        coor = vt.get_lidar_coor(*cam)
+        if coor_override is not None:
+            coor = coor_override(coor)
+        rb, rd, rf, st, ln = vt.voxel_pooling_prepare_v2(coor)
+        H, W = input_size[0] // downsample, input_size[1] // downsample
+        depth, feat = synthetic.make_depth_feat(B, N, vt.D, H, W, C, seed=seed)
+        bev = vt.voxel_pooling_v2(coor, depth, feat)
+        save(name,
+             grid_x=np.array(grid_config['x'], np.float64),
+             grid_y=np.array(grid_config['y'], np.float64),
+             grid_z=np.array(grid_config['z'], np.float64),
+             grid_depth=np.array(grid_config['depth'], np.float64),
+             input_size=np.array(input_size), downsample=np.array(downsample),
+             frustum=_np(vt.frustum), grid_size=_np(vt.grid_size),
+             grid_interval=_np(vt.grid_interval),
+             grid_lower_bound=_np(vt.grid_lower_bound),
+             dx=_np(vt.dx), bx=_np(vt.bx), nx=_np(vt.nx),
+             rots=_np(cam[0]), trans=_np(cam[1]), intrins=_np(cam[2]),
+             post_rots=_np(cam[3]), post_trans=_np(cam[4]), bda=_np(cam[5]),
+             coor=_np(coor), ranks_bev=_np(rb), ranks_depth=_np(rd),
+             ranks_feat=_np(rf), interval_starts=_np(st),
+             interval_lengths=_np(ln), depth=_np(depth), feat=_np(feat),
+             bev_feat=_np(bev.contiguous()),
+             bev_feat_shape=np.array(bev.shape))
+
+    # scaled-down shipped FB-OCC grid, 2 samples x 6 cameras
+    run_case('f_small_6cam',
+             dict(x=[-40, 40, 4.0], y=[-40, 40, 4.0], z=[-1, 5.4, 1.6],
+                  depth=[2.0, 42.0, 4.0]), (64, 176), 16, B=2, N=6, C=8, seed=3)
+    # scaled-down configs[0]: one camera, single-Z BEV
+    run_case('f_unit_1cam',
+             dict(x=[-51.2, 51.2, 3.2], y=[-51.2, 51.2, 3.2], z=[-5, 3, 8],
+                  depth=[1.0, 60.0, 1.0]), (32, 88), 4, B=1, N=1, C=5, seed=5)
+
+    # truncation-toward-zero quirk: coordinates in (-1, 0) are kept in cell 0
+    def jitter_box(coor):
+        g = torch.Generator().manual_seed(11)
+        lo = torch.tensor([-5.0, -5.0, -2.0])
+        hi = torch.tensor([5.0, 5.0, 2.0])
+        u = torch.rand(coor.shape, generator=g)
+        return lo - 1.5 + u * (hi - lo + 3.0)
+    run_case('f_negative_trunc',
+             dict(x=[-5, 5, 1.0], y=[-5, 5, 1.0], z=[-2, 2, 1.0],
+                  depth=[1.0, 5.0, 1.0]), (32, 32), 4, B=2, N=1, C=4, seed=7,
+             coor_override=jitter_box)
+
+    # nothing inside the grid -> the reference returns five None + zero volume
+    run_case('f_empty',
+             dict(x=[-5, 5, 1.0], y=[-5, 5, 1.0], z=[-2, 2, 1.0],
+                  depth=[1.0, 5.0, 1.0]), (32, 32), 4, B=1, N=1, C=4, seed=9,
+             coor_override=lambda c: c * 0 + 100.0)
+
+
+def main():
+    ref = ref_import.load_reference()
+    torch.manual_seed(0)
+    gen_forward(ref)
+    try:
+        import gen_golden_backward
+        gen_golden_backward.gen_backward(ref, save)
+    except ImportError:
+        print("gen_golden_backward.py not present yet; forward fixtures only")
+
+
+if __name__ == "__main__":
+    main()

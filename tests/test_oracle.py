@@ -1,0 +1,174 @@
+"""CPU tests: pin the oracle against the reference's own known-answer test and
+the golden vectors produced by the reference's Python (tests/golden/)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import canon_index, load_golden
+
+F_CASES = ["f_small_6cam", "f_unit_1cam", "f_negative_trunc"]
+
+
+def kat_inputs():
+    """The reference's only golden vector for the hot path:
+    mmdet3d/ops/bev_pool_v2/bev_pool.py:145-176 (test_bev_pool_v2)."""
+    depth = np.array([0.3, 0.4, 0.2, 0.1, 0.7, 0.6, 0.8, 0.9],
+                     np.float32).reshape(1, 1, 2, 2, 2)
+    feat = np.ones((1, 1, 2, 2, 2), np.float32)
+    ranks_depth = np.array([0, 4, 1, 6], np.int32)
+    ranks_feat = np.array([0, 0, 1, 2], np.int32)
+    ranks_bev = np.array([0, 0, 1, 1], np.int32)
+    interval_starts = np.array([0, 2], np.int32)
+    interval_lengths = np.array([2, 2], np.int32)
+    return (depth, feat, ranks_depth, ranks_feat, ranks_bev, (1, 1, 2, 2, 2),
+            interval_starts, interval_lengths)
+
+
+KAT_GRAD_DEPTH = np.array([2., 2., 0., 0., 2., 0., 2., 0.], np.float32)
+KAT_GRAD_FEAT = np.array([1.0, 1.0, 0.4, 0.4, 0.8, 0.8, 0., 0.], np.float32)
+
+
+def test_kat_forward(oracle_cpu):
+    args = kat_inputs()
+    out = oracle_cpu.bev_pool_v2(*args)
+    assert out.shape == (1, 2, 1, 2, 2)  # (B, C, Z, Y, X)
+    assert np.isclose(out.sum(), 4.4, rtol=0, atol=1e-6)  # bev_pool.py:169
+    # hand-derivable: voxel0 = .3+.7, voxel1 = .4+.8 for both channels
+    zyxc = oracle_cpu.bev_pool_v2_fwd(*args)
+    np.testing.assert_allclose(zyxc.reshape(4, 2)[0], [1.0, 1.0], atol=1e-7)
+    np.testing.assert_allclose(zyxc.reshape(4, 2)[1], [1.2, 1.2], atol=1e-6)
+    assert np.all(zyxc.reshape(4, 2)[2:] == 0)
+
+
+def test_kat_backward(oracle_cpu):
+    depth, feat, rd, rf, rb, shape, st, ln = kat_inputs()
+    og = np.ones(shape, np.float32)  # d(sum)/d(out)
+    dg, fg = oracle_cpu.bev_pool_v2_bwd(og, depth, feat, rd, rf, rb)
+    np.testing.assert_allclose(dg.ravel(), KAT_GRAD_DEPTH)  # :170-173
+    np.testing.assert_allclose(fg.ravel(), KAT_GRAD_FEAT, atol=1e-6)  # :174-176
+
+
+@pytest.mark.parametrize("case", F_CASES)
+def test_prepare_matches_reference_python(oracle_cpu, case):
+    g = load_golden(case)
+    rb, rd, rf, st, ln = oracle_cpu.voxel_prepare(
+        g["coor"], g["grid_lower_bound"], g["grid_interval"], g["grid_size"])
+    # bit-exact integer path
+    np.testing.assert_array_equal(rb, g["ranks_bev"])
+    np.testing.assert_array_equal(st, g["interval_starts"])
+    np.testing.assert_array_equal(ln, g["interval_lengths"])
+    a = canon_index(rb, rd, rf)
+    b = canon_index(g["ranks_bev"], g["ranks_depth"], g["ranks_feat"])
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    # the oracle's own order is the canonical (stable) one
+    for x, y in zip(a, (rb, rd, rf)):
+        np.testing.assert_array_equal(x, y)
+    # float32 rank arithmetic of the reference == exact integers below 2^24
+    rb1 = oracle_cpu.voxel_prepare(g["coor"], g["grid_lower_bound"],
+                                   g["grid_interval"], g["grid_size"],
+                                   rank_mode=1)[0]
+    np.testing.assert_array_equal(rb1, rb)
+
+
+def test_prepare_negative_truncation_keeps_cell0(oracle_cpu):
+    """`.long()` truncates toward zero: coordinates in (-1, 0) land in cell 0
+    and are KEPT (view_transformer.py:570-580)."""
+    g = load_golden("f_negative_trunc")
+    coor = g["coor"].reshape(-1, 3)
+    rel = (coor - g["grid_lower_bound"]) / g["grid_interval"]
+    inside_by_trunc = np.all((np.trunc(rel) >= 0) &
+                             (np.trunc(rel) < g["grid_size"]), axis=1)
+    inside_by_floor = np.all((np.floor(rel) >= 0) &
+                             (np.floor(rel) < g["grid_size"]), axis=1)
+    assert inside_by_trunc.sum() > inside_by_floor.sum()
+    assert len(g["ranks_bev"]) == inside_by_trunc.sum()
+
+
+def test_prepare_empty(oracle_cpu):
+    g = load_golden("f_empty")
+    out = oracle_cpu.voxel_prepare(g["coor"], g["grid_lower_bound"],
+                                   g["grid_interval"], g["grid_size"])
+    assert all(o is None for o in out)
+    assert "ranks_bev" not in g  # the reference returned None as well
+    assert np.all(g["bev_feat"] == 0)
+
+
+@pytest.mark.parametrize("case", F_CASES)
+def test_pool_matches_reference_glue(oracle_cpu, case):
+    """voxel_pooling_v2 (view_transformer.py:521-545) end to end."""
+    g = load_golden(case)
+    B, N, C, H, W = g["feat"].shape
+    gs = g["grid_size"].astype(int)
+    feat_nhwc = np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2))
+    out = oracle_cpu.bev_pool_v2(
+        g["depth"], feat_nhwc, g["ranks_depth"], g["ranks_feat"],
+        g["ranks_bev"], (B, gs[2], gs[1], gs[0], C), g["interval_starts"],
+        g["interval_lengths"])
+    bev = out.transpose(0, 1, 3, 4, 2)  # (B,C,Z,Y,X) -> (B,C,Y,X,Z)
+    assert tuple(g["bev_feat_shape"]) == bev.shape
+    np.testing.assert_array_equal(bev, g["bev_feat"])
+
+
+def test_float32_rank_overflow_documented(oracle_cpu):
+    """Above 2^24 voxels the reference's float32 rank arithmetic
+    (view_transformer.py:586-589) collides; the exact mode does not."""
+    lo = np.array([0, 0, 0], np.float32)
+    iv = np.array([1, 1, 1], np.float32)
+    gs = np.array([4096, 4096, 2], np.float32)  # 2^25 voxels
+    coor = np.array([[[[[[4092.5, 4095.5, 1.5], [4093.5, 4095.5, 1.5]]]]]],
+                    np.float32)  # (B=1,N=1,D=1,H=1,W=2,3)
+    exact = oracle_cpu.voxel_prepare(coor, lo, iv, gs, rank_mode=0)
+    f32 = oracle_cpu.voxel_prepare(coor, lo, iv, gs, rank_mode=1)
+    assert len(exact[3]) == 2          # two distinct voxels
+    assert len(f32[3]) == 1            # merged by float32 rounding
+
+
+def _rand_msda(seed, bs=2, nq=13, heads=4, ch=10, shapes=((5, 7), (3, 4)),
+               points=6):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.tensor(shapes, dtype=torch.long)
+    lsi = torch.cat((shapes_t.new_zeros(1), shapes_t.prod(1).cumsum(0)[:-1]))
+    n_value = int(shapes_t.prod(1).sum())
+    value = torch.randn(bs, n_value, heads, ch, generator=g)
+    # locations deliberately spill outside [0,1] to exercise zero padding
+    loc = torch.rand(bs, nq, heads, len(shapes), points, 2, generator=g) * 1.4 - 0.2
+    attw = torch.rand(bs, nq, heads, len(shapes), points, generator=g)
+    return value, shapes_t, lsi, loc, attw
+
+
+@pytest.mark.parametrize("ch", [10, 32])
+def test_msda_oracle_vs_grid_sample_and_hf(oracle_cpu, ch):
+    """The C im2col restatement == mmcv's documented PyTorch formulation
+    (grid_sample) == HF transformers' independent implementation."""
+    from oracle import torch_ref
+    value, shapes, lsi, loc, attw = _rand_msda(0, ch=ch)
+    c = oracle_cpu.msda_fwd(value.numpy(), shapes.numpy(), lsi.numpy(),
+                            loc.numpy(), attw.numpy())
+    t = torch_ref.multi_scale_deformable_attn_pytorch(value, shapes, loc, attw)
+    np.testing.assert_allclose(c, t.numpy(), rtol=0, atol=2e-5)
+    try:
+        from transformers.models.deformable_detr.modeling_deformable_detr \
+            import MultiScaleDeformableAttention as HF
+    except Exception:  # pragma: no cover
+        pytest.skip("transformers implementation not importable")
+    hf = HF()
+    shapes_list = [(int(h), int(w)) for h, w in shapes]
+    h = hf(value, shapes, shapes_list, lsi, loc, attw, 64)
+    np.testing.assert_allclose(c, h.detach().numpy(), rtol=0, atol=2e-5)
+
+
+def test_msda_backward_oracle_vs_autograd(oracle_cpu):
+    from oracle import torch_ref
+    value, shapes, lsi, loc, attw = _rand_msda(1)
+    value.requires_grad_(), loc.requires_grad_(), attw.requires_grad_()
+    out = torch_ref.multi_scale_deformable_attn_pytorch(value, shapes, loc,
+                                                        attw)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+    out.backward(go)
+    gv, gl, ga = oracle_cpu.msda_bwd(
+        value.detach().numpy(), shapes.numpy(), lsi.numpy(),
+        loc.detach().numpy(), attw.detach().numpy(), go.numpy())
+    np.testing.assert_allclose(gv, value.grad.numpy(), atol=5e-5)
+    np.testing.assert_allclose(ga, attw.grad.numpy(), atol=5e-5)
+    np.testing.assert_allclose(gl, loc.grad.numpy(), atol=5e-4)
