@@ -29,7 +29,7 @@ _SIGNATURES = {
     "fbbev_bev_pool_v2_fwd_dense": (
         ctypes.c_int, [_p] * 7 + [_i32, _p, _i32, _i32, _i64, _p, _p, _sz, _p]),
     "fbbev_bev_pool_v2_plan": (
-        ctypes.c_int, [_p, _p, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
+        ctypes.c_int, [_p, _p, _p, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
     "fbbev_bev_pool_v2_fwd_dense_planned": (
         ctypes.c_int, [_p] * 7 + [_i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
     "fbbev_bev_pool_v2_bwd": (ctypes.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p]),

@@ -23,6 +23,8 @@
 //    stores; empty voxels (79 % of a 200x200x16 grid) are stored as zeros
 //    straight from registers and never touch shared memory.  No atomics.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -30,6 +32,8 @@ namespace fbbev {
 
 constexpr int kPoolThreads = 256;
 constexpr int kPoolWarps = kPoolThreads / kWarp;
+constexpr int kGroup = 8;   // feat rows gathered ahead per warp
+constexpr int kMinPer = 4;  // minimum points per warp range
 
 // Sum of one interval for this lane's channels {lane, lane+32, ...}.
 // Point order == reference order (bev_pool_cuda.cu:36-40), one FMA per point
@@ -90,9 +94,9 @@ __global__ void __launch_bounds__(kPoolThreads) bev_pool_interval_kernel(
 }
 
 // ---------------------------------------------------------------------------
-// Plan: tile_first[t] = index of the first interval whose voxel rank lies in
-// tile t or later; tile_first[n_tiles] = n_intervals.  One thread per interval
-// fills the (usually empty) gap back to its predecessor's tile.
+// Plan: tile_pstart[t] = index of the first kept point whose voxel rank lies in
+// tile t or later; tile_pstart[n_tiles] = number of kept points.  One thread per
+// interval fills the (usually empty) gap back to its predecessor's tile.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int64_t tile_of(int64_t rank, int64_t zyx,
                                            int tiles_per_b, int T) {
@@ -102,50 +106,71 @@ __device__ __forceinline__ int64_t tile_of(int64_t rank, int64_t zyx,
 
 __global__ void bev_pool_plan_kernel(const int* __restrict__ ranks_bev,
                                      const int* __restrict__ interval_starts,
+                                     const int* __restrict__ interval_lengths,
                                      int n_intervals_max,
                                      const int* __restrict__ n_intervals_dev,
                                      int64_t zyx, int tiles_per_b, int T,
                                      int64_t n_tiles,
-                                     int* __restrict__ tile_first) {
+                                     int* __restrict__ tile_pstart) {
   const int n = n_intervals_dev ? min(*n_intervals_dev, n_intervals_max)
                                 : n_intervals_max;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   if (n <= 0) {
-    for (int64_t t = gid; t <= n_tiles; t += gsz) tile_first[t] = 0;
+    for (int64_t t = gid; t <= n_tiles; t += gsz) tile_pstart[t] = 0;
     return;
   }
   for (int64_t i = gid; i < n; i += gsz) {
-    int64_t t = tile_of(ranks_bev[interval_starts[i]], zyx, tiles_per_b, T);
+    const int ps = interval_starts[i];
+    int64_t t = tile_of(ranks_bev[ps], zyx, tiles_per_b, T);
     t = max((int64_t)0, min(t, n_tiles - 1));
     int64_t tp = -1;
     if (i > 0) {
       tp = tile_of(ranks_bev[interval_starts[i - 1]], zyx, tiles_per_b, T);
       tp = max((int64_t)0, min(tp, n_tiles - 1));
     }
-    for (int64_t u = tp + 1; u <= t; ++u) tile_first[u] = (int)i;
-    if (i == n - 1)
-      for (int64_t u = t + 1; u <= n_tiles; ++u) tile_first[u] = n;
+    for (int64_t u = tp + 1; u <= t; ++u) tile_pstart[u] = ps;
+    if (i == n - 1) {
+      const int pend = ps + interval_lengths[i];
+      for (int64_t u = t + 1; u <= n_tiles; ++u) tile_pstart[u] = pend;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
-// Dense pooling kernel: tile = T consecutive voxel ranks of one sample.
-// smem: slot[T] (int, -1 = empty voxel) | acc[<=T occupied voxels][cp] floats,
-// cp = C | 1 (odd pitch: phase-A lanes vary in channel, phase-B lanes vary in
-// slot -> both conflict-free).
+// Dense pooling kernel: a CTA owns T consecutive voxel ranks of one sample x all
+// C channels and writes them exactly once in (B,C,Z,Y,X) order.
+//
+// Phase A (gather): the tile's kept points [P0,P1) are split into NW contiguous
+//   ranges, one per warp.  A warp loads 32 (rank, depth index, feat index)
+//   triples with one coalesced load each -- a single dependent chain
+//   index -> depth -> feat row per 32 points -- and walks them in order, lanes
+//   owning channels {lane, lane+32, ..}.  A voxel's sum is kept in registers
+//   and stored to the voxel's shared-memory row when the rank changes (points
+//   are sorted by rank, so segments == the reference's intervals).  Segments cut
+//   by a range boundary are parked as head/tail partials and stitched in point
+//   order by one warp afterwards: deterministic, no atomics.
+// Phase B (stream out): one channel row = T contiguous floats; every lane
+//   assembles 4 consecutive voxels from the rows of occupied voxels (zeros
+//   come from registers, never from shared memory) and issues one 128-bit
+//   evict-first store.
+//
+// smem: occ[T] | rows[T][cp] | head[NW][cp] | tail[NW][cp] | meta[NW][4]
+// cp = C | 1 (odd pitch: phase-A lanes vary in channel -> conflict-free).
 // ---------------------------------------------------------------------------
-template <int T, int NCH>
-__global__ void __launch_bounds__(kPoolThreads) bev_pool_dense_kernel(
+template <int T, int NCH, int NW>
+__global__ void __launch_bounds__(NW * kWarp) bev_pool_dense_kernel(
     const float* __restrict__ depth, const float* __restrict__ feat,
     const int* __restrict__ ranks_depth, const int* __restrict__ ranks_feat,
-    const int* __restrict__ ranks_bev, const int* __restrict__ interval_starts,
-    const int* __restrict__ interval_lengths,
-    const int* __restrict__ tile_first, int c, int cp, int64_t zyx,
-    int tiles_per_b, int vec_ok, float* __restrict__ out) {
+    const int* __restrict__ ranks_bev, const int* __restrict__ tile_pstart,
+    int c, int cp, int64_t zyx, int tiles_per_b, int vec_ok,
+    float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int* slot = reinterpret_cast<int*>(smem_raw);
-  float* acc = reinterpret_cast<float*>(slot + T);
+  int* occ = reinterpret_cast<int*>(smem_raw);
+  float* rows = reinterpret_cast<float*>(occ + T);
+  float* head = rows + T * cp;
+  float* tail = head + NW * cp;
+  int* meta = reinterpret_cast<int*>(tail + NW * cp);  // [NW][4]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -153,97 +178,239 @@ __global__ void __launch_bounds__(kPoolThreads) bev_pool_dense_kernel(
   const int64_t v0 = (int64_t)(tile - b * tiles_per_b) * T;
   const int nv = (int)min((int64_t)T, zyx - v0);
   const int64_t rank0 = (int64_t)b * zyx + v0;
-  const int i0 = __ldg(tile_first + tile);
-  const int i1 = __ldg(tile_first + tile + 1);
-  const bool any = i1 > i0;
+  const int P0 = __ldg(tile_pstart + tile);
+  const int P1 = __ldg(tile_pstart + tile + 1);
+  const int n = P1 - P0;
+  const bool any = n > 0;
 
   if (any) {
-    if (tid < T) slot[tid] = -1;
+    // contiguous, nearly equal point ranges (every warp busy even when the tile
+    // holds few points)
+    const int per = max((n + NW - 1) / NW, kMinPer);
+    const int a = P0 + warp * per;
+    const int e = min(P1, a + per);
+    // first chunk's index words are requested before the barrier
+    int rbL = 0, rfL = 0, rdL = 0;
+    if (a + lane < e) {
+      rbL = __ldg(ranks_bev + a + lane);
+      rfL = __ldg(ranks_feat + a + lane);
+      rdL = __ldg(ranks_depth + a + lane);
+    }
+    bool cont_prev = false, cont_next = false;
+    if (a < e) {
+      if (a > P0) cont_prev = __ldg(ranks_bev + a - 1) == __ldg(ranks_bev + a);
+      if (e < P1) cont_next = __ldg(ranks_bev + e) == __ldg(ranks_bev + e - 1);
+    }
+    for (int i = tid; i < T; i += NW * kWarp) occ[i] = 0;
+    if (lane == 0) {
+      meta[warp * 4 + 0] = -1;  // head voxel
+      meta[warp * 4 + 1] = 0;   // head segment ends inside this range
+      meta[warp * 4 + 2] = -1;  // tail voxel
+    }
     __syncthreads();
-    // phase A: one warp per interval, sums staged in the interval's smem row
-    for (int i = i0 + warp; i < i1; i += kPoolWarps) {
-      const int start = __ldg(interval_starts + i);
-      const int len = __ldg(interval_lengths + i);
-      const int sl = i - i0;
-      const int64_t vl = (int64_t)__ldg(ranks_bev + start) - rank0;
-      float a[NCH];
-      interval_sum<NCH>(depth, feat, ranks_depth, ranks_feat, start, len, c,
-                        c, lane, a);
-      if (vl >= 0 && vl < nv && sl < T) {
-        if (lane == 0) slot[vl] = sl;
-        float* row = acc + sl * cp;
+
+    float acc[NCH];
+#pragma unroll
+    for (int r = 0; r < NCH; ++r) acc[r] = 0.f;
+    int cur_v = -1;
+    bool seg_head = false, first = true;
+
+    // store the finished segment (warp-uniform control flow)
+    auto flush = [&](bool continues) {
+      if (cur_v < 0) return;
+      float* dst = nullptr;
+      if (seg_head) {
+        dst = head + warp * cp;
+        if (lane == 0) {
+          meta[warp * 4 + 0] = cur_v;
+          meta[warp * 4 + 1] = continues ? 0 : 1;
+        }
+      } else if (continues) {
+        dst = tail + warp * cp;
+        if (lane == 0) meta[warp * 4 + 2] = cur_v;
+      } else if (cur_v < nv) {
+        dst = rows + cur_v * cp;
+        if (lane == 0) occ[cur_v] = 1;
+      }
+      if (dst) {
 #pragma unroll
         for (int r = 0; r < NCH; ++r) {
           const int ch = lane + kWarp * r;
-          if (ch < c) row[ch] = a[r];
+          if (ch < c) dst[ch] = acc[r];
+        }
+      }
+    };
+
+    for (int base = a; base < e; base += kWarp) {
+      const int cnt = min(kWarp, e - base);
+      if (base != a && lane < cnt) {
+        rbL = __ldg(ranks_bev + base + lane);
+        rfL = __ldg(ranks_feat + base + lane);
+        rdL = __ldg(ranks_depth + base + lane);
+      }
+      float dL = 0.f;
+      if (lane < cnt) dL = __ldg(depth + rdL);
+      const int vL = (int)((int64_t)rbL - rank0);
+      int prev = __shfl_up_sync(kFull, vL, 1);
+      if (lane == 0) prev = cur_v;
+      const unsigned starts = __ballot_sync(kFull, lane < cnt && vL != prev);
+      // points are consumed in groups of kGroup: all feat rows of a group are
+      // requested before the first one is used (independent gathers in
+      // flight), then folded into the running segment sum in point order
+      for (int kb = 0; kb < cnt; kb += kGroup) {
+        float fv[kGroup][NCH];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const int k = kb + j;  // shuffles must be executed by all lanes
+          const int rfk = __shfl_sync(kFull, rfL, k & 31);
+          const float* f = feat + (int64_t)rfk * c;
+#pragma unroll
+          for (int r = 0; r < NCH; ++r) {
+            const int ch = lane + kWarp * r;
+            fv[j][r] = (k < cnt && ch < c) ? __ldg(f + ch) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const int k = kb + j;
+          const float dk = __shfl_sync(kFull, dL, k & 31);
+          const int vk = __shfl_sync(kFull, vL, k & 31);
+          if (k < cnt) {
+            if ((starts >> k) & 1u) {
+              flush(false);
+              cur_v = vk;
+              seg_head = first && cont_prev;
+              first = false;
+#pragma unroll
+              for (int r = 0; r < NCH; ++r) acc[r] = 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < NCH; ++r) acc[r] = fmaf(fv[j][r], dk, acc[r]);
+          }
         }
       }
     }
-    __syncthreads();
+    flush(cont_next);
+
+    // stitch segments that straddle warp ranges, in point order
+    const int boundary = (a < e) && (cont_prev || cont_next);
+    if (__syncthreads_or(boundary)) {
+      if (warp == 0) {
+        float run[NCH];
+#pragma unroll
+        for (int r = 0; r < NCH; ++r) run[r] = 0.f;
+        for (int w = 0; w < NW; ++w) {
+          const int hv = meta[w * 4 + 0];
+          if (hv >= 0) {
+#pragma unroll
+            for (int r = 0; r < NCH; ++r) {
+              const int ch = lane + kWarp * r;
+              if (ch < c) run[r] += head[w * cp + ch];
+            }
+            if (meta[w * 4 + 1]) {  // segment complete
+              if (hv < nv) {
+                if (lane == 0) occ[hv] = 1;
+#pragma unroll
+                for (int r = 0; r < NCH; ++r) {
+                  const int ch = lane + kWarp * r;
+                  if (ch < c) rows[hv * cp + ch] = run[r];
+                }
+              }
+#pragma unroll
+              for (int r = 0; r < NCH; ++r) run[r] = 0.f;
+            }
+          }
+          if (meta[w * 4 + 2] >= 0) {
+#pragma unroll
+            for (int r = 0; r < NCH; ++r) {
+              const int ch = lane + kWarp * r;
+              if (ch < c) run[r] = tail[w * cp + ch];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
 
-  // phase B: stream the tile out, one channel row (T contiguous floats) at a
-  // time; (B,C,Z,Y,X): element (b, ch, v) at ((b*C + ch)*zyx + v)
+  // phase B: (B,C,Z,Y,X): element (b, ch, v) at ((b*C + ch)*zyx + v)
   float* obase = out + (int64_t)b * c * zyx + v0;
   if (vec_ok && nv == T) {
     constexpr int LPR = T / 4;          // lanes per channel row
     constexpr int RPW = kWarp / LPR;    // rows per warp instruction
     const int g = lane % LPR;
-    int4 s4 = make_int4(-1, -1, -1, -1);
-    if (any) s4 = *reinterpret_cast<const int4*>(slot + 4 * g);
-    const bool gany = (s4.x & s4.y & s4.z & s4.w) >= 0;
+    int4 o4 = make_int4(0, 0, 0, 0);
+    if (any) o4 = *reinterpret_cast<const int4*>(occ + 4 * g);
+    const bool gany = (o4.x | o4.y | o4.z | o4.w) != 0;
+    const float* r0 = rows + (4 * g) * cp;
     float* o = obase + 4 * g;
-    for (int row = warp * RPW + lane / LPR; row < c; row += kPoolWarps * RPW) {
+    for (int row = warp * RPW + lane / LPR; row < c; row += NW * RPW) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gany) {
-        if (s4.x >= 0) v.x = acc[s4.x * cp + row];
-        if (s4.y >= 0) v.y = acc[s4.y * cp + row];
-        if (s4.z >= 0) v.z = acc[s4.z * cp + row];
-        if (s4.w >= 0) v.w = acc[s4.w * cp + row];
+        if (o4.x) v.x = r0[row];
+        if (o4.y) v.y = r0[cp + row];
+        if (o4.z) v.z = r0[2 * cp + row];
+        if (o4.w) v.w = r0[3 * cp + row];
       }
       st_stream(reinterpret_cast<float4*>(o + (int64_t)row * zyx), v);
     }
   } else {
-    for (int row = warp; row < c; row += kPoolWarps) {
+    for (int row = warp; row < c; row += NW) {
       float* o = obase + (int64_t)row * zyx;
-      for (int v = lane; v < nv; v += kWarp) {
-        const int sl = any ? slot[v] : -1;
-        st_stream(o + v, sl >= 0 ? acc[sl * cp + row] : 0.f);
-      }
+      for (int v = lane; v < nv; v += kWarp)
+        st_stream(o + v, (any && occ[v]) ? rows[v * cp + row] : 0.f);
     }
   }
 }
 
 // --------------------------- host side ------------------------------------
-static inline int pick_tile(int c) {
-  // keep slot[] + acc[] within the 48 KB static-opt-in-free limit, >=4 CTAs/SM
+struct PoolShape {
+  int T, NW;
+};
+
+static inline size_t dense_smem_bytes(int T, int NW, int c) {
   const int cp = c | 1;
-  if ((size_t)128 * cp * 4 + 128 * 4 <= 46 * 1024) return 128;
-  if ((size_t)64 * cp * 4 + 64 * 4 <= 46 * 1024) return 64;
-  return 32;
+  return (size_t)T * 4 + (size_t)T * cp * 4 + (size_t)2 * NW * cp * 4 +
+         (size_t)NW * 16;
 }
 
-template <int T>
+// Tile shape: as many voxels per CTA as fit ~48 KB of shared memory (long
+// contiguous row stores), several CTAs per SM so one CTA's gather latency
+// hides behind the others' stores.  FBBEV_POOL_SHAPE="T,NW" overrides (tuning).
+static inline PoolShape pick_shape(int c) {
+  static const char* env = getenv("FBBEV_POOL_SHAPE");
+  if (env) {
+    int t = 0, w = 0;
+    if (sscanf(env, "%d,%d", &t, &w) == 2 &&
+        (t == 32 || t == 64 || t == 128) && (w == 4 || w == 8))
+      return {t, w};
+  }
+  if (dense_smem_bytes(128, 8, c) <= 48 * 1024) return {128, 8};
+  if (dense_smem_bytes(64, 8, c) <= 48 * 1024) return {64, 8};
+  return {32, 4};
+}
+static inline int pick_tile(int c) { return pick_shape(c).T; }
+
+template <int T, int NW>
 static int launch_dense(const float* depth, const float* feat,
                         const int* ranks_depth, const int* ranks_feat,
-                        const int* ranks_bev, const int* interval_starts,
-                        const int* interval_lengths, const int* tile_first,
-                        int c, int64_t zyx, int tiles_per_b, int64_t n_tiles,
+                        const int* ranks_bev, const int* tile_pstart, int c,
+                        int64_t zyx, int tiles_per_b, int64_t n_tiles,
                         int vec_ok, float* out, cudaStream_t st) {
   const int cp = c | 1;
-  const size_t smem = (size_t)T * 4 + (size_t)T * cp * 4;
+  const size_t smem = dense_smem_bytes(T, NW, c);
   const int nch = (c + kWarp - 1) / kWarp;
 #define FBBEV_DENSE_CASE(N)                                                   \
   {                                                                           \
-    auto k = bev_pool_dense_kernel<T, N>;                                     \
+    auto k = bev_pool_dense_kernel<T, N, NW>;                                 \
     if (smem > 48 * 1024) {                                                   \
       cudaError_t e = cudaFuncSetAttribute(                                   \
           k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (e != cudaSuccess) return (int)e;                                    \
     }                                                                         \
-    k<<<(unsigned)n_tiles, kPoolThreads, smem, st>>>(                         \
-        depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,     \
-        interval_lengths, tile_first, c, cp, zyx, tiles_per_b, vec_ok, out);  \
+    k<<<(unsigned)n_tiles, NW * kWarp, smem, st>>>(                           \
+        depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_pstart, c, cp,  \
+        zyx, tiles_per_b, vec_ok, out);                                       \
   }
   if (nch <= 1) FBBEV_DENSE_CASE(1)
   else if (nch <= 2) FBBEV_DENSE_CASE(2)
@@ -313,13 +480,14 @@ static int dense_check(int32_t n_intervals_max, int32_t c, int32_t batch,
 
 FBBEV_API int fbbev_bev_pool_v2_plan(
     const int32_t* ranks_bev, const int32_t* interval_starts,
-    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
+    const int32_t* interval_lengths, int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
     int32_t batch, int64_t n_voxels_per_sample, void* workspace,
     size_t workspace_bytes, fbbev_stream_t stream) {
   int rc = dense_check(n_intervals_max, c, batch, n_voxels_per_sample,
                        workspace, workspace, workspace_bytes);
   if (rc) return rc;
-  if (n_intervals_max > 0 && (!ranks_bev || !interval_starts))
+  if (n_intervals_max > 0 &&
+      (!ranks_bev || !interval_starts || !interval_lengths))
     return FBBEV_ERR_INVALID_ARGUMENT;
   const int64_t zyx = n_voxels_per_sample;
   const int T = pick_tile(c);
@@ -331,8 +499,9 @@ FBBEV_API int fbbev_bev_pool_v2_plan(
                                                     (int64_t)1 << 20);
   count_launch();
   bev_pool_plan_kernel<<<grid, threads, 0, as_stream(stream)>>>(
-      ranks_bev, interval_starts, n_intervals_max, n_intervals_dev, zyx,
-      tiles_per_b, T, n_tiles, static_cast<int*>(workspace));
+      ranks_bev, interval_starts, interval_lengths, n_intervals_max,
+      n_intervals_dev, zyx, tiles_per_b, T, n_tiles,
+      static_cast<int*>(workspace));
   return launch_status();
 }
 
@@ -355,24 +524,24 @@ FBBEV_API int fbbev_bev_pool_v2_fwd_dense_planned(
   const int T = pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
   const int64_t n_tiles = (int64_t)batch * tiles_per_b;
-  const int* tile_first = static_cast<const int*>(plan);
+  const int* tile_pstart = static_cast<const int*>(plan);
   const int vec_ok = (zyx % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const PoolShape shp = pick_shape(c);
   count_launch();
-  switch (T) {
-    case 128:
-      return launch_dense<128>(depth, feat, ranks_depth, ranks_feat, ranks_bev,
-                               interval_starts, interval_lengths, tile_first,
-                               c, zyx, tiles_per_b, n_tiles, vec_ok, out, st);
-    case 64:
-      return launch_dense<64>(depth, feat, ranks_depth, ranks_feat, ranks_bev,
-                              interval_starts, interval_lengths, tile_first, c,
-                              zyx, tiles_per_b, n_tiles, vec_ok, out, st);
-    default:
-      return launch_dense<32>(depth, feat, ranks_depth, ranks_feat, ranks_bev,
-                              interval_starts, interval_lengths, tile_first, c,
-                              zyx, tiles_per_b, n_tiles, vec_ok, out, st);
-  }
+#define FBBEV_SHAPE_CASE(TT, WW)                                              \
+  if (shp.T == TT && shp.NW == WW)                                            \
+    return launch_dense<TT, WW>(depth, feat, ranks_depth, ranks_feat,         \
+                                ranks_bev, tile_pstart, c, zyx, tiles_per_b,  \
+                                n_tiles, vec_ok, out, st);
+  FBBEV_SHAPE_CASE(128, 8)
+  FBBEV_SHAPE_CASE(128, 4)
+  FBBEV_SHAPE_CASE(64, 8)
+  FBBEV_SHAPE_CASE(64, 4)
+  FBBEV_SHAPE_CASE(32, 8)
+  FBBEV_SHAPE_CASE(32, 4)
+#undef FBBEV_SHAPE_CASE
+  return FBBEV_ERR_UNSUPPORTED;
 }
 
 FBBEV_API int fbbev_bev_pool_v2_fwd_dense(
@@ -382,7 +551,8 @@ FBBEV_API int fbbev_bev_pool_v2_fwd_dense(
     int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
     int32_t batch, int64_t n_voxels_per_sample, float* out, void* workspace,
     size_t workspace_bytes, fbbev_stream_t stream) {
-  int rc = fbbev_bev_pool_v2_plan(ranks_bev, interval_starts, n_intervals_max,
+  int rc = fbbev_bev_pool_v2_plan(ranks_bev, interval_starts,
+                                  interval_lengths, n_intervals_max,
                                   n_intervals_dev, c, batch,
                                   n_voxels_per_sample, workspace,
                                   workspace_bytes, stream);

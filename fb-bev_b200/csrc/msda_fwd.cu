@@ -163,6 +163,38 @@ __global__ void __launch_bounds__(kMsdaThreads) msda_fwd_kernel(
   store_head<CH>(out + bq * E + m * CH, acc);
 }
 
+// Any head width: one thread per output scalar (the reference's own
+// decomposition); used when CH is not one of the specialised widths, e.g. the
+// depth look-up launch of DA_MSDeformableAttention.forward (ch = depth bins).
+__global__ void __launch_bounds__(kMsdaThreads) msda_fwd_generic_kernel(
+    const float* __restrict__ value, const int64_t* __restrict__ shapes,
+    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+    const float* __restrict__ attw, int64_t n_out, int n_value, int heads,
+    int ch, int levels, int nq, int points, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out) return;  // idx = ((b*nq + q)*heads + m)*ch + c
+  const int c = (int)(idx % ch);
+  const int64_t item = idx / ch;
+  const int m = (int)(item % heads);
+  const int64_t bq = item / heads;
+  const int b = (int)(bq / nq);
+  const int E = heads * ch;
+  const int64_t wbase = item * levels * points;
+  float col = 0.f;
+  for (int l = 0; l < levels; ++l) {
+    const int H = (int)__ldg(shapes + 2 * l), W = (int)__ldg(shapes + 2 * l + 1);
+    const float* val =
+        value + ((int64_t)b * n_value + __ldg(lstart + l)) * E + m * ch + c;
+    for (int p = 0; p < points; ++p) {
+      const int64_t wi = wbase + (int64_t)l * points + p;
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + wi);
+      col += sample_scalar(val, H, W, E, pix(xy.y, H), pix(xy.x, W)) *
+             __ldg(attw + wi);
+    }
+  }
+  out[idx] = col;
+}
+
 // softmax statistics of one (b,q,head) logit row of n = levels*points entries
 __device__ __forceinline__ void softmax_stats(const float* __restrict__ lg,
                                               int n, float& mx, float& inv) {
@@ -336,6 +368,15 @@ FBBEV_API int fbbev_msda_fwd(const float* value, const int64_t* spatial_shapes,
   const unsigned grid = (unsigned)ceil_div64(n_items, kMsdaThreads);
   cudaStream_t st = as_stream(stream);
   count_launch();
+  if (!(ch == 4 || ch == 8 || ch == 10 || ch == 16 || ch == 20 || ch == 32 ||
+        ch == 64)) {
+    const int64_t n_out = n_items * ch;
+    msda_fwd_generic_kernel<<<(unsigned)ceil_div64(n_out, kMsdaThreads),
+                              kMsdaThreads, 0, st>>>(
+        value, spatial_shapes, level_start, loc, attw, n_out, n_value, heads,
+        ch, levels, nq, points, out);
+    return launch_status();
+  }
 #define FBBEV_LAUNCH(CHV)                                                    \
   msda_fwd_kernel<CHV><<<grid, kMsdaThreads, 0, st>>>(                       \
       value, spatial_shapes, level_start, loc, attw, n_items, n_value, heads, \

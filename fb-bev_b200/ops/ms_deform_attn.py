@@ -1,0 +1,168 @@
+"""Multi-scale deformable attention operators -- host-side mirror.
+
+* ``MultiScaleDeformableAttnFunction_fp32`` mirrors the reference's autograd
+  wrapper over mmcv's ``_ext`` op
+  (``.../bevformer_utils/multi_scale_deformable_attn_function.py:99-172``):
+  same ``apply(value, spatial_shapes, level_start_index, sampling_locations,
+  attention_weights, im2col_step)`` signature, fp32 forced as at :102.
+  ``MultiScaleDeformableAttnFunction_fp16`` maps to the same function, exactly
+  like the reference does at spatial_cross_attention_depth.py:580-583.
+* ``ms_deform_attn_fused`` / ``da_spatial_cross_attention_core`` expose the two
+  fused kernels (see ``include/fbbev_b200.h``).
+
+All compute is in ``libfbbev_b200.so``; CUDA tensors only.
+"""
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from .. import _lib
+
+__all__ = ['MultiScaleDeformableAttnFunction_fp32',
+           'MultiScaleDeformableAttnFunction_fp16', 'ms_deform_attn_forward',
+           'ms_deform_attn_fused', 'da_spatial_cross_attention_core']
+
+
+def _i64(t, dev):
+    return t.to(device=dev, dtype=torch.int64).contiguous()
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index,
+                           sampling_locations, attention_weights,
+                           im2col_step=64):
+    """Same contract as ``ext_module.ms_deform_attn_forward``
+    (multi_scale_deformable_attn_function.py:127-133).  ``im2col_step`` is
+    accepted and ignored (no batch-chunking restriction here)."""
+    dev = _lib.require_cuda(value, sampling_locations, attention_weights)
+    value = value.contiguous().float()
+    loc = sampling_locations.contiguous().float()
+    attw = attention_weights.contiguous().float()
+    ss, ls = _i64(spatial_shapes, dev), _i64(level_start_index, dev)
+    bs, n_value, heads, ch = value.shape
+    _, nq, _, levels, points, _ = loc.shape
+    out = value.new_empty((bs, nq, heads * ch))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fbbev_msda_fwd(
+            _lib.ptr(value), _lib.ptr(ss), _lib.ptr(ls), _lib.ptr(loc),
+            _lib.ptr(attw), bs, n_value, heads, ch, levels, nq, points,
+            _lib.ptr(out), _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_msda_fwd')
+    return out
+
+
+class MultiScaleDeformableAttnFunction_fp32(Function):
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                sampling_locations, attention_weights, im2col_step):
+        value = value.float()
+        sampling_locations = sampling_locations.float()
+        attention_weights = attention_weights.float()
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(
+            value, value_spatial_shapes, value_level_start_index,
+            sampling_locations, attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes,
+                              value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lstart, loc, attw = ctx.saved_tensors
+        dev = value.device
+        value, loc, attw = value.contiguous(), loc.contiguous(), \
+            attw.contiguous()
+        ss, ls = _i64(shapes, dev), _i64(lstart, dev)
+        grad_value = torch.zeros_like(value)
+        grad_loc = torch.zeros_like(loc)
+        grad_attw = torch.zeros_like(attw)
+        go = grad_output.contiguous().float()
+        bs, n_value, heads, ch = value.shape
+        _, nq, _, levels, points, _ = loc.shape
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fbbev_msda_bwd(
+                _lib.ptr(value), _lib.ptr(ss), _lib.ptr(ls), _lib.ptr(loc),
+                _lib.ptr(attw), _lib.ptr(go), bs, n_value, heads, ch, levels,
+                nq, points, _lib.ptr(grad_value), _lib.ptr(grad_loc),
+                _lib.ptr(grad_attw), _lib.stream_ptr(dev))
+        _lib.check(rc, 'fbbev_msda_bwd')
+        return grad_value, None, None, grad_loc, grad_attw, None
+
+
+# spatial_cross_attention_depth.py:580-583 maps both dtypes to the fp32 op
+MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction_fp32
+
+
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index,
+                         reference_points, sampling_offsets, attention_logits):
+    """softmax + location arithmetic + sampling of mmcv
+    ``MultiScaleDeformableAttention.forward`` in one kernel.
+
+    value (bs, n_value, heads, ch); reference_points (bs, nq, levels, 2);
+    sampling_offsets (bs, nq, heads, levels, points, 2) raw Linear output;
+    attention_logits (bs, nq, heads, levels, points) raw Linear output.
+    Returns (bs, nq, heads*ch).  Forward only (inference path)."""
+    dev = _lib.require_cuda(value, reference_points, sampling_offsets,
+                            attention_logits)
+    value = value.contiguous().float()
+    ref = reference_points.contiguous().float()
+    off = sampling_offsets.contiguous().float()
+    lg = attention_logits.contiguous().float()
+    ss, ls = _i64(spatial_shapes, dev), _i64(level_start_index, dev)
+    bs, n_value, heads, ch = value.shape
+    _, nq, _, levels, points, _ = off.shape
+    out = value.new_empty((bs, nq, heads * ch))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fbbev_msda_fused_fwd(
+            _lib.ptr(value), _lib.ptr(ss), _lib.ptr(ls), _lib.ptr(ref),
+            _lib.ptr(off), _lib.ptr(lg), bs, n_value, heads, ch, levels, nq,
+            points, _lib.ptr(out), _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_msda_fused_fwd')
+    return out
+
+
+def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
+                                    bev_query_depth, per_cam_mask,
+                                    sampling_offsets, attention_logits,
+                                    spatial_shapes, level_start_index, dbound,
+                                    num_Z_anchors):
+    """Fused depth-aware spatial cross-attention between the input Linears and
+    ``output_proj`` (spatial_cross_attention_depth.py:156-216, 540-595).
+
+    value (bs*n_cams, n_value, heads, ch)        value_proj(feat)
+    depth_prob (bs*n_cams, H0*W0, DC)            pred_img_depth, pixel-major
+    reference_points_cam (n_cams, bs, nq, Z, 2)
+    bev_query_depth (n_cams, bs, nq, Z[, 1])
+    per_cam_mask (n_cams, bs, nq, Z) bool
+    sampling_offsets (bs, nq, heads, levels, points, 2), attention_logits
+    (bs, nq, heads, levels, points): raw Linear outputs on the BEV queries.
+    Returns slots / clamp(count, 1): (bs, nq, heads*ch)."""
+    dev = _lib.require_cuda(value, depth_prob, reference_points_cam,
+                            bev_query_depth, per_cam_mask, sampling_offsets,
+                            attention_logits)
+    value = value.contiguous().float()
+    depth_prob = depth_prob.contiguous().float()
+    ref = reference_points_cam.contiguous().float()
+    rdep = bev_query_depth.contiguous().float()
+    mask = per_cam_mask.contiguous()
+    if mask.dtype != torch.uint8:
+        mask = mask.to(torch.uint8)
+    off = sampling_offsets.contiguous().float()
+    lg = attention_logits.contiguous().float()
+    ss, ls = _i64(spatial_shapes, dev), _i64(level_start_index, dev)
+    bn, n_value, heads, ch = value.shape
+    n_cams, bs, nq, Z, _ = ref.shape
+    assert bn == bs * n_cams and Z == num_Z_anchors
+    _, _, _, levels, points, _ = off.shape
+    DC = depth_prob.shape[-1]
+    out = value.new_empty((bs, nq, heads * ch))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fbbev_da_sca_fwd(
+            _lib.ptr(value), _lib.ptr(depth_prob), _lib.ptr(ref),
+            _lib.ptr(rdep), _lib.ptr(mask), _lib.ptr(off), _lib.ptr(lg),
+            _lib.ptr(ss), _lib.ptr(ls), _lib.c_floats(dbound), bs, n_cams, nq,
+            n_value, heads, ch, levels, points, Z, DC, _lib.ptr(out),
+            _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_da_sca_fwd')
+    return out

@@ -2,3 +2,4 @@
 ``mmdet3d/models/fbbev/view_transformation``).  Importing this package
 registers them (see ``registry.py``)."""
 from .forward_projection import *  # noqa: F401,F403
+from .backward_projection import *  # noqa: F401,F403

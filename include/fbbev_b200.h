@@ -99,6 +99,7 @@ int fbbev_bev_pool_v2_fwd_dense(
  */
 int fbbev_bev_pool_v2_plan(const int32_t* ranks_bev,
                            const int32_t* interval_starts,
+                           const int32_t* interval_lengths,
                            int32_t n_intervals_max,
                            const int32_t* n_intervals_dev, int32_t c,
                            int32_t batch, int64_t n_voxels_per_sample,

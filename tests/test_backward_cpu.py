@@ -1,0 +1,80 @@
+"""CPU tests of the host-side mirror of the backward projection: state-dict
+keys, registry/config contract and the plain-PyTorch geometry must equal the
+reference's own Python (golden fixtures from tests/golden/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from bp_common import bp_cfg_from_golden, build_bp, cam_params
+from conftest import load_golden
+
+CASES = ["b_bp_e80_1lvl", "b_bp_e64_3lvl"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_state_dict_keys_and_shapes_match_reference(case):
+    from fbbev_b200.registry import build_head
+    g = load_golden(case)
+    bp = build_head(bp_cfg_from_golden(g))
+    ref = {k[4:]: v.shape for k, v in g.items() if k.startswith("sd::")}
+    mine = {k: tuple(v.shape) for k, v in bp.state_dict().items()}
+    assert set(mine) == set(ref)
+    for k in ref:
+        assert mine[k] == tuple(ref[k]), k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_point_sampling_bit_exact(case):
+    """bevformer_encoder.get_reference_points / point_sampling
+    (bevformer_encoder.py:52-120) on CPU == the reference's tensors."""
+    g, bp = build_bp(case)
+    enc = bp.transformer.encoder
+    bev_h, bev_w = int(g["bev_h"]), int(g["bev_w"])
+    ref_3d = enc.get_reference_points(bev_h, bev_w, dim='3d', device='cpu')
+    _, ref_cam, mask, depth = enc.point_sampling(ref_3d, enc.pc_range, None,
+                                                 cam_params=cam_params(g))
+    np.testing.assert_array_equal(ref_cam.numpy(), g["reference_points_cam"])
+    np.testing.assert_array_equal(mask.numpy(), g["per_cam_mask"])
+    np.testing.assert_array_equal(depth.numpy(), g["bev_query_depth"])
+    ref_2d = enc.get_reference_points(bev_h, bev_w, dim='2d', bs=2,
+                                      device='cpu')
+    assert ref_2d.shape == (2, bev_h * bev_w, 1, 2)
+    assert torch.allclose(ref_2d[0, 0, 0], torch.tensor([0.5 / bev_w,
+                                                         0.5 / bev_h]))
+
+
+def test_positional_encoding_and_init():
+    from fbbev_b200.view_transformation.backward_projection import (
+        CustormLearnedPositionalEncoding, DA_MSDeformableAttention,
+        MultiScaleDeformableAttention)
+    pe = CustormLearnedPositionalEncoding(40, 100, 100)
+    out = pe(2, 100, 100, 'cpu')
+    assert out.shape == (2, 80, 100, 100)
+    assert torch.equal(out[0, :40, 3, 7], pe.col_embed.weight[7])
+    assert torch.equal(out[1, 40:, 3, 7], pe.row_embed.weight[3])
+    # sampling-offset bias: ring direction per head, radius p+1, anchors share
+    da = DA_MSDeformableAttention(embed_dims=80, num_points=8, num_levels=1)
+    b = da.sampling_offsets.bias.view(8, 1, 2, 4, 2)
+    assert torch.allclose(b[0, 0, 0, :, :], torch.tensor([1.0, 0.0]).expand(4, 2))
+    assert torch.allclose(b[0, 0, 1, :, :], torch.tensor([2.0, 0.0]).expand(4, 2))
+    assert torch.all(da.sampling_offsets.weight == 0)
+    assert torch.all(da.attention_weights.weight == 0)
+    assert da.output_proj is None
+    sa = MultiScaleDeformableAttention(embed_dims=80, num_levels=1)
+    b = sa.sampling_offsets.bias.view(8, 1, 4, 2)
+    assert torch.allclose(b[2, 0, 3], torch.tensor([0.0, 4.0]), atol=1e-6)
+
+
+def test_layer_injects_batch_first_and_builds_from_config():
+    """custom_base_transformer_layer.py:132-136 injects batch_first into every
+    attention config; FFN embed_dims defaults to the layer's."""
+    g = load_golden(CASES[0])
+    from fbbev_b200.registry import build_head
+    bp = build_head(bp_cfg_from_golden(g))
+    layer = bp.transformer.encoder.layers[0]
+    assert layer.attentions[0].batch_first is True
+    assert layer.attentions[1].batch_first is True
+    assert layer.attentions[1].deformable_attention.num_Z_anchors == 4
+    assert layer.operation_order[0] == 'self_attn' and not layer.pre_norm
+    assert len(layer.norms) == 3 and len(layer.ffns) == 1
+    assert layer.ffns[0].layers[0][0].out_features == 4 * int(g["E"])

@@ -1,0 +1,163 @@
+"""GPU parity tests of the backward projection (depth-aware spatial
+cross-attention).  CUDA results come through the C ABI and are compared with
+
+* the golden fixtures recorded from the reference's own Python classes
+  (mmcv's MSDA kernel served by the C oracle) -- tests/golden/b_*.npz;
+* the C oracle / torch grid_sample restatement on seeded random inputs.
+
+Tolerance 1e-4 absolute (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from bp_common import build_bp, cam_params
+from conftest import load_golden
+from test_oracle import _rand_msda
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ATOL = 1e-4
+CASES = ["b_bp_e80_1lvl", "b_bp_e64_3lvl"]
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("ch", [3, 4, 8, 10, 16, 20, 32, 40, 64])
+def test_msda_forward_vs_oracle(oracle_cpu, ch):
+    from fbbev_b200.ops.ms_deform_attn import ms_deform_attn_forward
+    value, shapes, lsi, loc, attw = _rand_msda(ch, ch=ch, nq=37)
+    want = oracle_cpu.msda_fwd(value.numpy(), shapes.numpy(), lsi.numpy(),
+                               loc.numpy(), attw.numpy())
+    got = ms_deform_attn_forward(value.to(DEV), shapes.to(DEV), lsi.to(DEV),
+                                 loc.to(DEV), attw.to(DEV), 64)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-5)
+
+
+def test_msda_edge_locations(oracle_cpu):
+    """Locations on / outside the border, NaN and huge values: zero padding and
+    the (-1, H) x (-1, W) validity window of the im2col algorithm."""
+    from fbbev_b200.ops.ms_deform_attn import ms_deform_attn_forward
+    value, shapes, lsi, loc, attw = _rand_msda(3, bs=1, nq=16, points=4)
+    special = torch.tensor([0.0, 1.0, -1e-3, 1.0 + 1e-3, -0.2, 1.2, 1e9, -1e9,
+                            0.5 / 7, 1 - 0.5 / 7])
+    flat = loc.view(-1, 2)
+    flat[:len(special), 0] = special
+    flat[len(special):2 * len(special), 1] = special
+    flat[40, 0] = float('nan')
+    flat[41, 1] = float('inf')
+    want = oracle_cpu.msda_fwd(value.numpy(), shapes.numpy(), lsi.numpy(),
+                               loc.numpy(), attw.numpy())
+    got = ms_deform_attn_forward(value.to(DEV), shapes.to(DEV), lsi.to(DEV),
+                                 loc.to(DEV), attw.to(DEV))
+    assert np.isfinite(want).all()
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("ch", [10, 12])
+def test_msda_backward_vs_oracle(oracle_cpu, ch):
+    from fbbev_b200.ops.ms_deform_attn import \
+        MultiScaleDeformableAttnFunction_fp32
+    value, shapes, lsi, loc, attw = _rand_msda(5, ch=ch, nq=29)
+    v = value.to(DEV).requires_grad_()
+    l = loc.to(DEV).requires_grad_()
+    a = attw.to(DEV).requires_grad_()
+    out = MultiScaleDeformableAttnFunction_fp32.apply(v, shapes.to(DEV),
+                                                      lsi.to(DEV), l, a, 64)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+    out.backward(go.to(DEV))
+    gv, gl, ga = oracle_cpu.msda_bwd(value.numpy(), shapes.numpy(),
+                                     lsi.numpy(), loc.numpy(), attw.numpy(),
+                                     go.numpy())
+    np.testing.assert_allclose(v.grad.cpu().numpy(), gv, rtol=0, atol=5e-5)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), ga, rtol=0, atol=5e-5)
+    np.testing.assert_allclose(l.grad.cpu().numpy(), gl, rtol=0, atol=5e-4)
+
+
+def test_fused_self_attention_core_vs_unfused(oracle_cpu):
+    """fbbev_msda_fused_fwd == softmax + loc arithmetic + ms_deform_attn."""
+    from fbbev_b200.ops.ms_deform_attn import ms_deform_attn_fused
+    value, shapes, lsi, loc, attw = _rand_msda(7, ch=10, nq=50, points=4)
+    bs, nq, heads, levels, points, _ = loc.shape
+    g = torch.Generator().manual_seed(8)
+    ref = torch.rand(bs, nq, levels, 2, generator=g)
+    off = torch.randn(bs, nq, heads, levels, points, 2, generator=g) * 2
+    logits = torch.randn(bs, nq, heads, levels, points, generator=g)
+    wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+    loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    w = logits.flatten(3).softmax(-1).view_as(logits)
+    want = oracle_cpu.msda_fwd(value.numpy(), shapes.numpy(), lsi.numpy(),
+                               loc.numpy(), w.numpy())
+    got = ms_deform_attn_fused(value.to(DEV), shapes.to(DEV), lsi.to(DEV),
+                               ref.to(DEV), off.to(DEV), logits.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_da_sca_vs_reference_golden(case):
+    """One DA_SpatialCrossAttention.forward on the reference's recorded inputs
+    (its own query / masks / reference points) == the reference's output."""
+    g, bp = build_bp(case, DEV)
+    sca = bp.transformer.encoder.layers[0].attentions[1]
+    with torch.no_grad():
+        out = sca(t(g["sca_query"]), t(g["sca_key"]), t(g["sca_key"]), None,
+                  query_pos=t(g["sca_query_pos"]),
+                  reference_points_cam=t(g["reference_points_cam"]),
+                  spatial_shapes=t(g["spatial_shapes"]),
+                  level_start_index=t(g["level_start_index"]),
+                  bev_query_depth=t(g["bev_query_depth"]),
+                  pred_img_depth=t(g["depth"]),
+                  per_cam_mask_list=t(g["per_cam_mask"]))
+    np.testing.assert_allclose(out.cpu().numpy(), g["sca_out"], rtol=0,
+                               atol=ATOL)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_da_sca_rebatch_path_equals_fused(case):
+    """The reference-shaped re-batching path (used when a bev_mask is given)
+    and the fused kernel agree; an all-true bev_mask must change nothing."""
+    g, bp = build_bp(case, DEV)
+    sca = bp.transformer.encoder.layers[0].attentions[1]
+    kw = dict(query_pos=t(g["sca_query_pos"]),
+              reference_points_cam=t(g["reference_points_cam"]),
+              spatial_shapes=t(g["spatial_shapes"]),
+              level_start_index=t(g["level_start_index"]),
+              bev_query_depth=t(g["bev_query_depth"]),
+              pred_img_depth=t(g["depth"]),
+              per_cam_mask_list=t(g["per_cam_mask"]))
+    q, k = t(g["sca_query"]), t(g["sca_key"])
+    with torch.no_grad():
+        fused = sca(q, k, k, None, **kw)
+        mask = torch.ones(q.shape[:2], dtype=torch.bool, device=DEV)
+        rebatch = sca(q, k, k, None, bev_mask=mask, **kw)
+    assert (fused - rebatch).abs().max().item() <= ATOL
+    np.testing.assert_allclose(rebatch.cpu().numpy(), g["sca_out"], rtol=0,
+                               atol=ATOL)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_backward_projection_vs_reference_golden(case):
+    """Whole BackwardProjection.forward (embedding + pos-enc + BEVFormer +
+    encoder geometry + self-attn + LN + DA-SCA + LN + FFN + LN) with the
+    reference's weights == the reference's output."""
+    g, bp = build_bp(case, DEV)
+    n_lvl = len(g["level_shapes"])
+    mlvl = [t(g[f"feat{i}"]) for i in range(n_lvl)]
+    with torch.no_grad():
+        out = bp(mlvl, None, lss_bev=t(g["lss_bev"]),
+                 cam_params=cam_params(g, DEV), pred_img_depth=t(g["depth"]))
+    assert tuple(out.shape) == g["out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0,
+                               atol=5e-4)
+    # geometry on the device agrees with the reference's CPU tensors
+    enc = bp.transformer.encoder
+    ref_3d = enc.get_reference_points(int(g["bev_h"]), int(g["bev_w"]),
+                                      dim='3d', device=DEV)
+    _, ref_cam, mask, depth = enc.point_sampling(
+        ref_3d, enc.pc_range, None, cam_params=cam_params(g, DEV))
+    agree = (mask.cpu().numpy() == g["per_cam_mask"]).mean()
+    assert agree >= 0.999
+    vis = g["per_cam_mask"]
+    np.testing.assert_allclose(ref_cam.cpu().numpy()[vis],
+                               g["reference_points_cam"][vis], atol=1e-4)

@@ -156,7 +156,12 @@ def test_dense_pool_vs_oracle(oracle_cpu, name, batch):
     # reference-layout drop-in kernel: same numbers, (B,Z,Y,X,C)
     ref_layout = QuickCumsumCuda.apply(depth, feat_nhwc, rd, rf, rb, shape, st,
                                        ln)
-    assert torch.equal(ref_layout.permute(0, 4, 1, 2, 3), got)
+    np.testing.assert_allclose(ref_layout.cpu().numpy(),
+                               want.transpose(0, 2, 3, 4, 1), rtol=0,
+                               atol=ATOL)
+    # (voxels whose points straddle two warps of the dense kernel are summed
+    # as two partials, so the two kernels agree to rounding, not bit for bit)
+    assert (ref_layout.permute(0, 4, 1, 2, 3) - got).abs().max().item() <= ATOL
     # sync-free plugin path (padded buffers + device counts) == trimmed path
     bev = vt(cam, feat, depth)
     assert torch.equal(bev, got.permute(0, 1, 3, 4, 2))
@@ -179,9 +184,12 @@ def test_vs_reference_cuda_kernel(name):
     torch.cuda.synchronize()
     err = (got - want).abs().max().item()
     assert err <= ATOL, err
-    if name != "unit_128":
-        # identical summation order for short intervals -> identical bits
-        assert torch.equal(got, want)
+    # the drop-in interval kernel keeps the reference's summation order:
+    # identical bits
+    from fbbev_b200.ops.bev_pool_v2 import QuickCumsumCuda
+    same_order = QuickCumsumCuda.apply(depth, feat_nhwc, rd, rf, rb, shape, st,
+                                       ln).permute(0, 4, 1, 2, 3)
+    assert torch.equal(same_order, want)
 
 
 def test_backward_vs_oracle_and_reference_kernel(oracle_cpu):
@@ -296,4 +304,4 @@ def test_wide_channels(oracle_cpu):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=ATOL)
     ref_layout = QuickCumsumCuda.apply(*args, shape, st.to(DEV),
                                        ln.int().to(DEV))
-    assert torch.equal(ref_layout.permute(0, 4, 1, 2, 3), got)
+    assert (ref_layout.permute(0, 4, 1, 2, 3) - got).abs().max().item() <= ATOL

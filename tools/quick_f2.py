@@ -1,0 +1,54 @@
+"""Cold vs L2-warm timing of the dense pooling kernel and of prep+plan+pool."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fbbev_b200 import synthetic, _lib
+from fbbev_b200.ops import bev_pool_v2 as ops
+from fbbev_b200.view_transformation.forward_projection import LSSViewTransformerFunction3D
+dev = "cuda:0"
+vt = LSSViewTransformerFunction3D(synthetic.GRID_CONFIGS["fbocc_200"], (256, 704), 16)
+cam = synthetic.make_cam_params(1, 6, (256, 704), device=dev)
+depth, feat = synthetic.make_depth_feat(1, 6, vt.D, 16, 44, 80, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+coor = vt.get_lidar_coor(*cam)
+idx = vt.prepare_index(coor)
+rb, rd, rf, st, ln = idx.trimmed()
+feat_nhwc = feat.permute(0, 1, 3, 4, 2).contiguous()
+shape = vt._bev_feat_shape(depth, feat_nhwc)
+zyx = shape[1]*shape[2]*shape[3]
+L = _lib.lib()
+ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(1, zyx)
+ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+out = torch.empty((1, 80, shape[1], shape[2], shape[3]), device=dev)
+sp = _lib.stream_ptr(torch.device(dev))
+L.fbbev_bev_pool_v2_plan(_lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), None, 80, 1, zyx, _lib.ptr(ws), ws_bytes, sp)
+def planned():
+    L.fbbev_bev_pool_v2_fwd_dense_planned(_lib.ptr(depth), _lib.ptr(feat_nhwc), _lib.ptr(rd), _lib.ptr(rf), _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), 80, 1, zyx, _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
+def touch():
+    for t in (rb, rd, rf, depth, feat_nhwc, ws): t.sum()
+def timeit(fn, pre=None, iters=30):
+    for _ in range(5): fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        if pre: pre()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort(); return ts[len(ts)//2]
+print("kernel cold (flush, inputs in DRAM)      %.1f us" % timeit(planned))
+print("kernel inputs L2-warm (flush then touch) %.1f us" % timeit(planned, pre=touch))
+def noflush(fn, iters=30):
+    for _ in range(5): fn()
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(iters): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e3 / iters
+print("kernel back-to-back no flush             %.1f us" % noflush(planned))
+print("memset back-to-back no flush             %.1f us" % noflush(lambda: out.zero_()))
+def f_all():
+    i2 = vt.prepare_index(coor)
+    return ops.bev_pool_v2_dense(depth, feat_nhwc, i2.ranks_depth, i2.ranks_feat, i2.ranks_bev, shape, i2.interval_starts, i2.interval_lengths, n_intervals_dev=i2.n_intervals_dev)
+print("prep+plan+pool cold                      %.1f us" % timeit(f_all))
+print("prep+plan+pool back-to-back              %.1f us" % noflush(f_all))
