@@ -25,13 +25,17 @@ _SIGNATURES = {
     "fbbev_debug_launch_count": (ctypes.c_longlong, []),
     "fbbev_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "fbbev_bev_pool_v2_fwd": (ctypes.c_int, [_p] * 7 + [_i32, _i32, _p, _p]),
-    "fbbev_bev_pool_v2_dense_workspace_bytes": (_sz, [_i32, _i64]),
+    "fbbev_bev_pool_v2_dense_workspace_bytes": (
+        _sz, [_i32, _i64, _i32, _i32, _i32]),
     "fbbev_bev_pool_v2_fwd_dense": (
-        ctypes.c_int, [_p] * 7 + [_i32, _p, _i32, _i32, _i64, _p, _p, _sz, _p]),
+        ctypes.c_int,
+        [_p] * 7 + [_i32, _p, _i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
     "fbbev_bev_pool_v2_plan": (
-        ctypes.c_int, [_p, _p, _p, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
+        ctypes.c_int,
+        [_p, _p, _p, _i32, _p, _i32, _i32, _i32, _i64, _p, _sz, _p]),
     "fbbev_bev_pool_v2_fwd_dense_planned": (
-        ctypes.c_int, [_p] * 7 + [_i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
+        ctypes.c_int,
+        [_p] * 7 + [_i32, _i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
     "fbbev_bev_pool_v2_bwd": (ctypes.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p]),
     "fbbev_bev_pool_v2_bwd_bczyx": (
         ctypes.c_int, [_p] * 8 + [_i32, _i32, _i64, _p, _p, _p]),

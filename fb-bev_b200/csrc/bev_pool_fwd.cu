@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "bev_pool_split.h"
 #include "common.cuh"
 
 namespace fbbev {
@@ -391,6 +392,16 @@ static inline PoolShape pick_shape(int c) {
 }
 static inline int pick_tile(int c) { return pick_shape(c).T; }
 
+// FBBEV_POOL_KERNEL: 0 = fused one-tile-per-CTA kernel (any shape), 1 (default)
+// = two-kernel path of bev_pool_split.cu when C % 4 == 0 and Z*Y*X % 4 == 0.
+static inline int pool_kernel_mode() {
+  static const char* env = getenv("FBBEV_POOL_KERNEL");
+  return env ? atoi(env) : 1;
+}
+static inline bool use_split(int c, int64_t zyx) {
+  return pool_kernel_mode() == 1 && split_supported(c, zyx);
+}
+
 template <int T, int NW>
 static int launch_dense(const float* depth, const float* feat,
                         const int* ranks_depth, const int* ranks_feat,
@@ -458,38 +469,53 @@ FBBEV_API int fbbev_bev_pool_v2_fwd(
 }
 
 FBBEV_API size_t fbbev_bev_pool_v2_dense_workspace_bytes(
-    int32_t batch, int64_t n_voxels_per_sample) {
-  if (batch <= 0 || n_voxels_per_sample <= 0) return 0;
-  // sized for the smallest tile (32 voxels): n_tiles + 1 ints
+    int32_t batch, int64_t n_voxels_per_sample, int32_t n_intervals_max,
+    int32_t n_points, int32_t c) {
+  if (batch <= 0 || n_voxels_per_sample <= 0 || n_intervals_max < 0 ||
+      n_points < 0 || c <= 0)
+    return 0;
+  // sized for the smallest tile (32 voxels): n_tiles + 1 ints; the two-kernel
+  // path adds one rank word and one C-float row per interval
   const int64_t tiles = (int64_t)batch * ceil_div64(n_voxels_per_sample, 32);
-  return (size_t)(tiles + 1) * sizeof(int32_t);
+  const size_t fused = (size_t)(tiles + 1) * sizeof(int32_t);
+  return std::max(fused, split_workspace_bytes(batch, n_voxels_per_sample,
+                                               n_intervals_max, n_points, c));
 }
 
-static int dense_check(int32_t n_intervals_max, int32_t c, int32_t batch,
-                       int64_t zyx, const void* out, const void* workspace,
-                       size_t workspace_bytes) {
-  if (n_intervals_max < 0 || c <= 0 || batch <= 0 || zyx <= 0)
+static int dense_check(int32_t n_intervals_max, int32_t n_points, int32_t c,
+                       int32_t batch, int64_t zyx, const void* out,
+                       const void* workspace, size_t workspace_bytes) {
+  if (n_intervals_max < 0 || n_points < n_intervals_max || c <= 0 ||
+      batch <= 0 || zyx <= 0)
     return FBBEV_ERR_INVALID_ARGUMENT;
   if ((int64_t)batch * zyx > (int64_t)INT32_MAX) return FBBEV_ERR_UNSUPPORTED;
   if (c > 16 * kWarp) return FBBEV_ERR_UNSUPPORTED;
   if (!out || !workspace) return FBBEV_ERR_INVALID_ARGUMENT;
-  if (workspace_bytes < fbbev_bev_pool_v2_dense_workspace_bytes(batch, zyx))
+  if (workspace_bytes <
+      fbbev_bev_pool_v2_dense_workspace_bytes(batch, zyx, n_intervals_max,
+                                              n_points, c))
     return FBBEV_ERR_WORKSPACE_TOO_SMALL;
   return FBBEV_OK;
 }
 
 FBBEV_API int fbbev_bev_pool_v2_plan(
     const int32_t* ranks_bev, const int32_t* interval_starts,
-    const int32_t* interval_lengths, int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
+    const int32_t* interval_lengths, int32_t n_intervals_max,
+    const int32_t* n_intervals_dev, int32_t n_points, int32_t c,
     int32_t batch, int64_t n_voxels_per_sample, void* workspace,
     size_t workspace_bytes, fbbev_stream_t stream) {
-  int rc = dense_check(n_intervals_max, c, batch, n_voxels_per_sample,
-                       workspace, workspace, workspace_bytes);
+  int rc = dense_check(n_intervals_max, n_points, c, batch,
+                       n_voxels_per_sample, workspace, workspace,
+                       workspace_bytes);
   if (rc) return rc;
   if (n_intervals_max > 0 &&
       (!ranks_bev || !interval_starts || !interval_lengths))
     return FBBEV_ERR_INVALID_ARGUMENT;
   const int64_t zyx = n_voxels_per_sample;
+  if (use_split(c, zyx))
+    return split_plan(ranks_bev, interval_starts, interval_lengths,
+                      n_intervals_max, n_intervals_dev, n_points, c, batch,
+                      zyx, workspace, as_stream(stream));
   const int T = pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
   const int64_t n_tiles = (int64_t)batch * tiles_per_b;
@@ -509,11 +535,11 @@ FBBEV_API int fbbev_bev_pool_v2_fwd_dense_planned(
     const float* depth, const float* feat, const int32_t* ranks_depth,
     const int32_t* ranks_feat, const int32_t* ranks_bev,
     const int32_t* interval_starts, const int32_t* interval_lengths,
-    int32_t n_intervals_max, int32_t c, int32_t batch,
-    int64_t n_voxels_per_sample, float* out, const void* plan,
-    size_t plan_bytes, fbbev_stream_t stream) {
-  int rc = dense_check(n_intervals_max, c, batch, n_voxels_per_sample, out,
-                       plan, plan_bytes);
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, float* out, void* plan, size_t plan_bytes,
+    fbbev_stream_t stream) {
+  int rc = dense_check(n_intervals_max, n_points, c, batch,
+                       n_voxels_per_sample, out, plan, plan_bytes);
   if (rc) return rc;
   if (n_intervals_max > 0 &&
       (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev ||
@@ -521,6 +547,10 @@ FBBEV_API int fbbev_bev_pool_v2_fwd_dense_planned(
     return FBBEV_ERR_INVALID_ARGUMENT;
   cudaStream_t st = as_stream(stream);
   const int64_t zyx = n_voxels_per_sample;
+  if (use_split(c, zyx))
+    return split_launch(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                        interval_starts, interval_lengths, n_intervals_max,
+                        n_points, c, batch, zyx, out, plan, st);
   const int T = pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
   const int64_t n_tiles = (int64_t)batch * tiles_per_b;
@@ -548,17 +578,17 @@ FBBEV_API int fbbev_bev_pool_v2_fwd_dense(
     const float* depth, const float* feat, const int32_t* ranks_depth,
     const int32_t* ranks_feat, const int32_t* ranks_bev,
     const int32_t* interval_starts, const int32_t* interval_lengths,
-    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
-    int32_t batch, int64_t n_voxels_per_sample, float* out, void* workspace,
-    size_t workspace_bytes, fbbev_stream_t stream) {
+    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t n_points,
+    int32_t c, int32_t batch, int64_t n_voxels_per_sample, float* out,
+    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
   int rc = fbbev_bev_pool_v2_plan(ranks_bev, interval_starts,
                                   interval_lengths, n_intervals_max,
-                                  n_intervals_dev, c, batch,
+                                  n_intervals_dev, n_points, c, batch,
                                   n_voxels_per_sample, workspace,
                                   workspace_bytes, stream);
   if (rc) return rc;
   return fbbev_bev_pool_v2_fwd_dense_planned(
       depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
-      interval_lengths, n_intervals_max, c, batch, n_voxels_per_sample, out,
-      workspace, workspace_bytes, stream);
+      interval_lengths, n_intervals_max, n_points, c, batch,
+      n_voxels_per_sample, out, workspace, workspace_bytes, stream);
 }

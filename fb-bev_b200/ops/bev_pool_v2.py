@@ -87,6 +87,12 @@ class QuickCumsumCuda(torch.autograd.Function):
         return depth_grad, feat_grad, None, None, None, None, None, None
 
 
+# Optional instrumentation: when set to an object with ``before(stream)`` /
+# ``after(stream)`` methods, they are called around the launch of the dense
+# pooling kernel (bench.py uses it to bracket that one kernel with CUDA events).
+KERNEL_HOOK = None
+
+
 def _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                    bev_feat_shape, interval_starts, interval_lengths,
                    n_intervals_dev):
@@ -96,17 +102,30 @@ def _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     assert feat.shape[-1] == C, (feat.shape, bev_feat_shape)
     L = _lib.lib()
     out = torch.empty((B, C, Z, Y, X), dtype=torch.float32, device=dev)
-    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, Z * Y * X)
+    n_points = ranks_bev.shape[0]
+    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(
+        B, Z * Y * X, interval_lengths.shape[0], n_points, C)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    hook = KERNEL_HOOK
     with torch.cuda.device(dev):
-        rc = L.fbbev_bev_pool_v2_fwd_dense(
+        sp = _lib.stream_ptr(dev)
+        rc = L.fbbev_bev_pool_v2_plan(
+            _lib.ptr(ranks_bev), _lib.ptr(interval_starts),
+            _lib.ptr(interval_lengths), interval_lengths.shape[0],
+            _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X, _lib.ptr(ws),
+            ws_bytes, sp)
+        _lib.check(rc, 'fbbev_bev_pool_v2_plan')
+        if hook is not None:
+            hook.before()
+        rc = L.fbbev_bev_pool_v2_fwd_dense_planned(
             _lib.ptr(depth), _lib.ptr(feat), _lib.ptr(ranks_depth),
             _lib.ptr(ranks_feat), _lib.ptr(ranks_bev),
             _lib.ptr(interval_starts), _lib.ptr(interval_lengths),
-            interval_lengths.shape[0], _lib.ptr(n_intervals_dev), C, B,
-            Z * Y * X, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
-            _lib.stream_ptr(dev))
-    _lib.check(rc, 'fbbev_bev_pool_v2_fwd_dense')
+            interval_lengths.shape[0], n_points, C, B, Z * Y * X,
+            _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
+        if hook is not None:
+            hook.after()
+    _lib.check(rc, 'fbbev_bev_pool_v2_fwd_dense_planned')
     return out
 
 

@@ -1,0 +1,54 @@
+"""Frame sharding of the view transformation across ranks.
+
+Both halves of the path are independent per sample/frame: the batch index is
+only the top term of the voxel rank (view_transformer.py:573-575, 586-587) and
+the cross-attention processes ``bs * num_cams`` independent camera batches
+(spatial_cross_attention_depth.py:190-206).  So frames are split across ranks
+(one process per GPU) and NO collective sits on the data path; cameras of one
+frame stay together because the cross-attention averages over the cameras that
+see a query (:213-216).
+
+The reference has no collective on this path either.
+``gather_bev`` is the optional exchange for a consumer that needs every frame's
+BEV on every rank: one ``all_gather_into_tensor`` of the refined 2-D BEV
+(B, C, bev_h, bev_w) -- 16x smaller than the voxel volume, which stays sharded.
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ['frame_slice', 'shard_frames', 'gather_bev']
+
+
+def frame_slice(n_frames, rank, world_size):
+    """Contiguous, balanced split: rank r owns frames [lo, hi)."""
+    base, extra = divmod(n_frames, world_size)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def shard_frames(tensors, rank, world_size, dim=0):
+    """Slice every tensor of a (nested) tuple/list along the frame dim."""
+    if isinstance(tensors, torch.Tensor):
+        lo, hi = frame_slice(tensors.shape[dim], rank, world_size)
+        return tensors.narrow(dim, lo, hi - lo)
+    return type(tensors)(shard_frames(t, rank, world_size, dim)
+                         for t in tensors)
+
+
+def gather_bev(local_bev, group=None):
+    """All-gather per-rank BEV tensors (b_local, C, H, W) along the frame dim.
+
+    Every rank must hold the same number of local frames (pad the last shard
+    if the frame count is not divisible).  Works on NCCL (CUDA tensors) and
+    gloo (CPU tensors, used by the CPU tests)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return local_bev
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_bev
+    local_bev = local_bev.contiguous()
+    out = local_bev.new_empty((world * local_bev.shape[0],) +
+                              tuple(local_bev.shape[1:]))
+    dist.all_gather_into_tensor(out, local_bev, group=group)
+    return out

@@ -78,40 +78,45 @@ int fbbev_bev_pool_v2_fwd(const float* depth, const float* feat,
  * n_intervals_dev: optional device int32 holding the live interval count
  *   (<= n_intervals_max); NULL means n_intervals_max is the count.  This lets
  *   the prepare -> pool chain run without a host sync / under CUDA graphs.
+ * n_points = number of entries in ranks_bev / ranks_depth / ranks_feat (an
+ *   upper bound of the kept points when the buffers are over-allocated).
  * n_voxels_per_sample = Z*Y*X.  Requires B*Z*Y*X < 2^31 (int32 ranks).
  * workspace: >= fbbev_bev_pool_v2_dense_workspace_bytes(...) bytes.
  */
 size_t fbbev_bev_pool_v2_dense_workspace_bytes(int32_t batch,
-                                               int64_t n_voxels_per_sample);
+                                               int64_t n_voxels_per_sample,
+                                               int32_t n_intervals_max,
+                                               int32_t n_points, int32_t c);
 int fbbev_bev_pool_v2_fwd_dense(
     const float* depth, const float* feat, const int32_t* ranks_depth,
     const int32_t* ranks_feat, const int32_t* ranks_bev,
     const int32_t* interval_starts, const int32_t* interval_lengths,
-    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t c,
-    int32_t batch, int64_t n_voxels_per_sample, float* out, void* workspace,
-    size_t workspace_bytes, fbbev_stream_t stream);
+    int32_t n_intervals_max, const int32_t* n_intervals_dev, int32_t n_points,
+    int32_t c, int32_t batch, int64_t n_voxels_per_sample, float* out,
+    void* workspace, size_t workspace_bytes, fbbev_stream_t stream);
 
 /*
  * The two halves of fbbev_bev_pool_v2_fwd_dense, for callers that reuse an
  * index (static camera rig, `accelerate=True`, view_transformer.py:261-283):
- * `plan` builds the tile table for a given (index, C) once; `_planned` is then
- * a single kernel launch per forward.
+ * `plan` builds the tile table for a given (index, C) once; `_planned` then
+ * runs only the pooling kernels (the workspace doubles as their scratch, so it
+ * is written by `_planned` as well; one workspace per concurrent stream).
  */
 int fbbev_bev_pool_v2_plan(const int32_t* ranks_bev,
                            const int32_t* interval_starts,
                            const int32_t* interval_lengths,
                            int32_t n_intervals_max,
-                           const int32_t* n_intervals_dev, int32_t c,
-                           int32_t batch, int64_t n_voxels_per_sample,
-                           void* workspace, size_t workspace_bytes,
-                           fbbev_stream_t stream);
+                           const int32_t* n_intervals_dev, int32_t n_points,
+                           int32_t c, int32_t batch,
+                           int64_t n_voxels_per_sample, void* workspace,
+                           size_t workspace_bytes, fbbev_stream_t stream);
 int fbbev_bev_pool_v2_fwd_dense_planned(
     const float* depth, const float* feat, const int32_t* ranks_depth,
     const int32_t* ranks_feat, const int32_t* ranks_bev,
     const int32_t* interval_starts, const int32_t* interval_lengths,
-    int32_t n_intervals_max, int32_t c, int32_t batch,
-    int64_t n_voxels_per_sample, float* out, const void* plan,
-    size_t plan_bytes, fbbev_stream_t stream);
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, float* out, void* plan, size_t plan_bytes,
+    fbbev_stream_t stream);
 
 /*
  * Drop-in for `bev_pool_v2_ext.bev_pool_v2_backward`

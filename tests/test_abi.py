@@ -33,8 +33,8 @@ def test_abi_version_and_error_strings():
     assert L.fbbev_abi_version() == 1
     assert L.fbbev_error_string(0) == b"ok"
     assert b"workspace" in L.fbbev_error_string(-2)
-    assert L.fbbev_bev_pool_v2_dense_workspace_bytes(1, 640000) >= 4 * (
-        640000 // 32 + 1)
+    assert L.fbbev_bev_pool_v2_dense_workspace_bytes(1, 640000, 1000, 2000, 80) >= 4 * (
+        640000 // 32 + 1) + 1000 * 80 * 4
     assert L.fbbev_voxel_prepare_workspace_bytes(1000, 5000) > 0
 
 

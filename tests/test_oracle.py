@@ -172,3 +172,33 @@ def test_msda_backward_oracle_vs_autograd(oracle_cpu):
     np.testing.assert_allclose(gv, value.grad.numpy(), atol=5e-5)
     np.testing.assert_allclose(ga, attw.grad.numpy(), atol=5e-5)
     np.testing.assert_allclose(gl, loc.grad.numpy(), atol=5e-4)
+
+
+@pytest.mark.parametrize("case", ["b_bp_e80_1lvl", "b_bp_e64_3lvl"])
+def test_backward_projection_cpu_oracle_vs_reference_golden(case):
+    """oracle/backward_ref.py (the CPU restatement used as the checker of the
+    fused CUDA kernel and as bench.py's CPU baseline) reproduces the output of
+    the reference's own BackwardProjection / DA_SpatialCrossAttention."""
+    from bp_common import build_bp, cam_params
+    from oracle import backward_ref
+    g, bp = build_bp(case)
+    n_lvl = len(g["level_shapes"])
+    mlvl = [torch.from_numpy(g[f"feat{i}"]) for i in range(n_lvl)]
+    out = backward_ref.backward_projection_cpu(
+        bp, mlvl, torch.from_numpy(g["lss_bev"]), cam_params(g),
+        torch.from_numpy(g["depth"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=2e-5)
+    # the cross-attention alone, on the reference's recorded inputs
+    sca = bp.transformer.encoder.layers[0].attentions[1]
+    with backward_ref._cpu_kernels(), torch.no_grad():
+        o = sca(torch.from_numpy(g["sca_query"]),
+                torch.from_numpy(g["sca_key"]), torch.from_numpy(g["sca_key"]),
+                None, query_pos=torch.from_numpy(g["sca_query_pos"]),
+                reference_points_cam=torch.from_numpy(
+                    g["reference_points_cam"]),
+                spatial_shapes=torch.from_numpy(g["spatial_shapes"]),
+                level_start_index=torch.from_numpy(g["level_start_index"]),
+                bev_query_depth=torch.from_numpy(g["bev_query_depth"]),
+                pred_img_depth=torch.from_numpy(g["depth"]),
+                per_cam_mask_list=torch.from_numpy(g["per_cam_mask"]))
+    np.testing.assert_allclose(o.numpy(), g["sca_out"], rtol=0, atol=2e-5)

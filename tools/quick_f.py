@@ -40,13 +40,13 @@ res["geometry(torch)"] = timeit(lambda: vt.get_lidar_coor(*cam))
 res["prepare"] = timeit(lambda: vt.prepare_index(coor))
 res["pool_dense(plan+kernel)"] = timeit(lambda: ops.bev_pool_v2(depth, feat_nhwc, rd, rf, rb, shape, st, ln))
 L = _lib.lib()
-ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(shape[0], shape[1]*shape[2]*shape[3])
+ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(shape[0], shape[1]*shape[2]*shape[3], len(st), len(rb), 80)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 out = torch.empty((shape[0], 80, shape[1], shape[2], shape[3]), device=dev)
 sp = _lib.stream_ptr(torch.device(dev))
-L.fbbev_bev_pool_v2_plan(_lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), None, 80, shape[0], shape[1]*shape[2]*shape[3], _lib.ptr(ws), ws_bytes, sp)
+L.fbbev_bev_pool_v2_plan(_lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), None, len(rb), 80, shape[0], shape[1]*shape[2]*shape[3], _lib.ptr(ws), ws_bytes, sp)
 def planned():
-    L.fbbev_bev_pool_v2_fwd_dense_planned(_lib.ptr(depth), _lib.ptr(feat_nhwc), _lib.ptr(rd), _lib.ptr(rf), _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), 80, shape[0], shape[1]*shape[2]*shape[3], _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
+    L.fbbev_bev_pool_v2_fwd_dense_planned(_lib.ptr(depth), _lib.ptr(feat_nhwc), _lib.ptr(rd), _lib.ptr(rf), _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), len(rb), 80, shape[0], shape[1]*shape[2]*shape[3], _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
 res["pool_dense(kernel only)"] = timeit(planned)
 res["pool_interval(ref layout, +zeros)"] = timeit(lambda: ops.QuickCumsumCuda.apply(depth, feat_nhwc, rd, rf, rb, shape, st, ln))
 res["memset_only(out.zero_)"] = timeit(lambda: out.zero_())

@@ -17,13 +17,13 @@ feat_nhwc = feat.permute(0, 1, 3, 4, 2).contiguous()
 shape = vt._bev_feat_shape(depth, feat_nhwc)
 zyx = shape[1]*shape[2]*shape[3]
 L = _lib.lib()
-ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(1, zyx)
+ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(1, zyx, len(st), len(rb), 80)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 out = torch.empty((1, 80, shape[1], shape[2], shape[3]), device=dev)
 sp = _lib.stream_ptr(torch.device(dev))
-L.fbbev_bev_pool_v2_plan(_lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), None, 80, 1, zyx, _lib.ptr(ws), ws_bytes, sp)
+L.fbbev_bev_pool_v2_plan(_lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), None, len(rb), 80, 1, zyx, _lib.ptr(ws), ws_bytes, sp)
 def planned():
-    L.fbbev_bev_pool_v2_fwd_dense_planned(_lib.ptr(depth), _lib.ptr(feat_nhwc), _lib.ptr(rd), _lib.ptr(rf), _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), 80, 1, zyx, _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
+    L.fbbev_bev_pool_v2_fwd_dense_planned(_lib.ptr(depth), _lib.ptr(feat_nhwc), _lib.ptr(rd), _lib.ptr(rf), _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), len(st), len(rb), 80, 1, zyx, _lib.ptr(out), _lib.ptr(ws), ws_bytes, sp)
 def touch():
     for t in (rb, rd, rf, depth, feat_nhwc, ws): t.sum()
 def timeit(fn, pre=None, iters=30):
