@@ -9,18 +9,30 @@
 //    ~55 % busy (37-51 M warp instructions) and long-scoreboard / barrier stalls:
 //    index chasing (tile table -> index words -> depth / feat rows) inside the
 //    CTA that owns the 40 KB output tile starves the store stream.
-// So the index chasing is moved out of the writer:
+// So the index chasing is moved out of the CTA that owns an output tile, and
+// both kinds of work run in ONE launch as producer / consumer CTAs:
 //
-//  K1  interval_sums   warp w folds the 32 kept points [32w, 32w+32): coalesced
-//      index loads, batched depth / feat gathers, one FMA per point and channel
-//      in point order; interval sums go to compact rows V[interval][C] (43 MB
-//      for the 200x200x16 grid, consumed by K2 while still in L2), the part of
-//      an interval that spills into later slices to carry rows X[slice][C].
-//  K2  dense_write     a CTA owns T consecutive voxel ranks x all C channels:
-//      it copies the rows of its (contiguous) intervals V[i0:i1] into shared
-//      memory with cp.async -- two dependent loads in total, all coalesced --
-//      and streams the tile out channel row by channel row with 128-bit
-//      evict-first stores; empty voxels are stored as register zeros.
+//  producers (blockIdx < n_sum_ctas) -- "interval sums": warp w folds the 32
+//      kept points [32w, 32w+32) -- perfectly balanced, so the dense voxels next
+//      to a camera (up to 63 points on the 200x200x16 grid, thousands on the
+//      1-camera 128x128 grid: the reference kernel's and every tile-owning
+//      kernel's tail) are spread over many warps.  Coalesced index loads; every
+//      run of equal voxel rank is folded by a 4-lane group (8 runs per warp
+//      instruction) with 128-bit feat loads and one FMA per point and channel
+//      in point order (bev_pool_cuda.cu:36-40).  Interval sums go to compact
+//      rows V[interval][C] (43 MB for the 200x200x16 grid; they never leave
+//      L2), the part of an interval that spills into later slices to carry rows
+//      X[slice][C].  A producer CTA publishes a flag when its rows are written.
+//  consumers (the other CTAs) -- "dense write": a CTA owns T consecutive voxel
+//      ranks x all C channels.  Empty tiles stream zeros at once; the others
+//      wait for the flags of the (one or two) producers that cover their
+//      points, copy the rows of their contiguous intervals V[i0:i1] into shared
+//      memory with cp.async, add carry rows in slice order, and stream the tile
+//      out channel row by channel row with 128-bit evict-first stores.
+//  Producers have the lowest block indices, so they are resident before any
+//  consumer can wait on them; consumers never block producers.
+//  Every output element and every V / X row is written exactly once; no
+//  floating-point atomics; results are deterministic.
 //
 // Requires C % 4 == 0 and (Z*Y*X) % 4 == 0, 16-byte aligned out.
 #include <algorithm>
@@ -30,8 +42,9 @@
 
 namespace fbbev {
 
-constexpr int kSumThreads = 256;
-constexpr int kWrThreads = 128;
+constexpr int kPoolThreads = 256;  // both roles
+constexpr int kSumThreads = kPoolThreads;
+constexpr int kWrThreads = kPoolThreads;
 constexpr int kWrWarps = kWrThreads / kWarp;
 
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
@@ -121,8 +134,8 @@ __global__ void split_plan_kernel(
 // slice's carry row X[w] and is added, in slice order, by K2.  Every row is
 // written exactly once; no atomics; deterministic.
 template <int LG, int VPL>
-__global__ void __launch_bounds__(kSumThreads) interval_sums_kernel(
-    const float* __restrict__ depth, const float* __restrict__ feat,
+__device__ __forceinline__ void interval_sums_role(
+    int cta, const float* __restrict__ depth, const float* __restrict__ feat,
     const int* __restrict__ ranks_depth, const int* __restrict__ ranks_feat,
     const int* __restrict__ ranks_bev, const int* __restrict__ interval_starts,
     const int* __restrict__ warp_first, const int* __restrict__ meta, int c,
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(kSumThreads) interval_sums_kernel(
   __shared__ int s_rf[WPC][kPtsPerWarp];
   __shared__ float s_d[WPC][kPtsPerWarp];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int64_t w = (int64_t)blockIdx.x * WPC + wi;
+  const int64_t w = (int64_t)cta * WPC + wi;
   if (w >= meta[2]) return;
   const int n = meta[0];
   const int base = (int)w * kPtsPerWarp;
@@ -196,13 +209,20 @@ __global__ void __launch_bounds__(kSumThreads) interval_sums_kernel(
 // ---------------------------- K2: dense write ------------------------------
 // smem: rows[<=T][c + 4] | slot[T] (0 = empty voxel, else row + 1)
 //       | carry_lo[T], carry_n[T] (carry rows X[lo+1 .. lo+n] of each interval)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int T>
-__global__ void __launch_bounds__(kWrThreads) dense_write_kernel(
-    const float* __restrict__ V, const float* __restrict__ X,
+__device__ __forceinline__ void dense_write_role(
+    int tile, const float* __restrict__ V, const float* __restrict__ X,
     const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
     const int* __restrict__ interval_starts,
-    const int* __restrict__ interval_lengths, int c, int64_t zyx,
-    int tiles_per_b, float* __restrict__ out) {
+    const int* __restrict__ interval_lengths, const int* __restrict__ meta,
+    const int* __restrict__ flags, int c, int64_t zyx, int tiles_per_b,
+    float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int pitch = c + 4;  // 16-byte aligned rows
   float* rows = reinterpret_cast<float*>(smem_raw);              // [T][pitch]
@@ -211,7 +231,6 @@ __global__ void __launch_bounds__(kWrThreads) dense_write_kernel(
   int* carry_n = carry_lo + T;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x;
   const int b = tile / tiles_per_b;
   const int64_t v0 = (int64_t)(tile - b * tiles_per_b) * T;
   const int nv = (int)min((int64_t)T, zyx - v0);
@@ -235,6 +254,15 @@ __global__ void __launch_bounds__(kWrThreads) dense_write_kernel(
         st_stream(reinterpret_cast<float4*>(o), z);
     return;
   }
+  // wait for the producers that fold this tile's points
+  if (tid == 0) {
+    const int pa = __ldg(interval_starts + i0);
+    const int pb = i1 < meta[0] ? __ldg(interval_starts + i1) : meta[1];
+    constexpr int kPtsPerCta = kPtsPerWarp * (kSumThreads / kWarp);
+    for (int f = pa / kPtsPerCta; f <= (pb - 1) / kPtsPerCta; ++f)
+      while (ld_acquire(flags + f) == 0) __nanosleep(64);
+  }
+  __syncthreads();
   // rows of this tile's intervals: contiguous in V, copied asynchronously
   {
     const float4* src = reinterpret_cast<const float4*>(V) + (int64_t)i0 * c4;
@@ -275,7 +303,7 @@ __global__ void __launch_bounds__(kWrThreads) dense_write_kernel(
         float4 t[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          t[j] = (k + j < nx) ? __ldg(src + (int64_t)(k + j) * c4)
+          t[j] = (k + j < nx) ? __ldcg(src + (int64_t)(k + j) * c4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -310,6 +338,37 @@ __global__ void __launch_bounds__(kWrThreads) dense_write_kernel(
   }
 }
 
+// ------------------------- one launch, two roles ---------------------------
+template <int T, int LG, int VPL>
+__global__ void __launch_bounds__(kPoolThreads) pool_split_kernel(
+    const float* __restrict__ depth, const float* __restrict__ feat,
+    const int* __restrict__ ranks_depth, const int* __restrict__ ranks_feat,
+    const int* __restrict__ ranks_bev, const int* __restrict__ interval_starts,
+    const int* __restrict__ interval_lengths,
+    const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
+    const int* __restrict__ warp_first, const int* __restrict__ meta,
+    int* __restrict__ flags, int n_sum_ctas, int c, int64_t zyx,
+    int tiles_per_b, float* __restrict__ V, float* __restrict__ X,
+    float* __restrict__ out) {
+  if ((int)blockIdx.x < n_sum_ctas) {
+    interval_sums_role<LG, VPL>(blockIdx.x, depth, feat, ranks_depth,
+                                ranks_feat, ranks_bev, interval_starts,
+                                warp_first, meta, c, V, X);
+    // publish: every thread's row stores, then the flag
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + blockIdx.x),
+                   "r"(1)
+                   : "memory");
+    }
+    return;
+  }
+  dense_write_role<T>(blockIdx.x - n_sum_ctas, V, X, tile_first, seg_rank,
+                      interval_starts, interval_lengths, meta, flags, c, zyx,
+                      tiles_per_b, out);
+}
+
 // ------------------------------ host side ---------------------------------
 static inline size_t write_smem_bytes(int T, int c) {
   return (size_t)T * (c + 4) * 4 + (size_t)3 * T * 4;
@@ -339,9 +398,10 @@ struct SplitWs {
   int* seg_rank;
   int* warp_first;
   int* meta;
-  float* V;   // [n_intervals_max][c]  interval sums
-  float* X;   // [n_warps_max][c]      carry rows of K1 slices
-  int n_warps_max;
+  int* flags;  // [n_sum_ctas] producer-done flags (cleared per launch)
+  float* V;    // [n_intervals_max][c]  interval sums
+  float* X;    // [n_warps_max][c]      carry rows of producer slices
+  int n_warps_max, n_sum_ctas;
   size_t bytes;
 };
 
@@ -356,10 +416,13 @@ static SplitWs split_layout(void* ws, int batch, int64_t zyx,
   w.seg_rank = reinterpret_cast<int*>(p + off);
   off += up256((size_t)std::max(n_intervals_max, 1) * 4);
   w.n_warps_max = (int)ceil_div64(std::max(n_points_max, 1), kPtsPerWarp);
+  w.n_sum_ctas = (int)ceil_div64(w.n_warps_max, kSumThreads / kWarp);
   w.warp_first = reinterpret_cast<int*>(p + off);
   off += up256((size_t)(w.n_warps_max + 1) * 4);
   w.meta = reinterpret_cast<int*>(p + off);
   off += 256;
+  w.flags = reinterpret_cast<int*>(p + off);
+  off += up256((size_t)w.n_sum_ctas * 4);
   w.V = reinterpret_cast<float*>(p + off);
   off += up256((size_t)std::max(n_intervals_max, 1) * c * 4);
   w.X = reinterpret_cast<float*>(p + off);
@@ -397,69 +460,88 @@ int split_plan(const int* ranks_bev, const int* interval_starts,
   return launch_status();
 }
 
-template <int T>
-static int launch_write(const SplitWs& w, const int* interval_starts,
-                        const int* interval_lengths, int c, int64_t zyx,
-                        int tiles_per_b, int64_t n_tiles, float* out,
-                        cudaStream_t st) {
+template <int T, int LG, int VPL>
+static int launch_pool(const SplitWs& w, const float* depth, const float* feat,
+                       const int* ranks_depth, const int* ranks_feat,
+                       const int* ranks_bev, const int* interval_starts,
+                       const int* interval_lengths, int n_sum_ctas, int c,
+                       int64_t zyx, int tiles_per_b, int64_t n_tiles,
+                       float* out, cudaStream_t st) {
   const size_t smem = write_smem_bytes(T, c);
-  auto k = dense_write_kernel<T>;
+  auto k = pool_split_kernel<T, LG, VPL>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(
         k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  k<<<(unsigned)n_tiles, kWrThreads, smem, st>>>(
-      w.V, w.X, w.tile_first, w.seg_rank, interval_starts, interval_lengths, c,
-      zyx, tiles_per_b, out);
+  k<<<(unsigned)(n_sum_ctas + n_tiles), kPoolThreads, smem, st>>>(
+      depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+      interval_lengths, w.tile_first, w.seg_rank, w.warp_first, w.meta,
+      w.flags, n_sum_ctas, c, zyx, tiles_per_b, w.V, w.X, out);
   return launch_status();
+}
+
+template <int T>
+static int launch_pool_t(const SplitWs& w, const float* depth,
+                         const float* feat, const int* ranks_depth,
+                         const int* ranks_feat, const int* ranks_bev,
+                         const int* interval_starts,
+                         const int* interval_lengths, int n_sum_ctas, int c,
+                         int64_t zyx, int tiles_per_b, int64_t n_tiles,
+                         float* out, cudaStream_t st) {
+  const int c4 = c / 4;
+#define FBBEV_POOL_CASE(LGV, VPLV)                                            \
+  return launch_pool<T, LGV, VPLV>(w, depth, feat, ranks_depth, ranks_feat,   \
+                                   ranks_bev, interval_starts,                \
+                                   interval_lengths, n_sum_ctas, c, zyx,      \
+                                   tiles_per_b, n_tiles, out, st)
+  // group width LG and float4 columns per lane VPL with LG * VPL >= C / 4
+  if (c4 <= 4) FBBEV_POOL_CASE(4, 1);
+  if (c4 <= 8) FBBEV_POOL_CASE(4, 2);
+  if (c4 <= 16) FBBEV_POOL_CASE(4, 4);
+  if (c4 <= 20) FBBEV_POOL_CASE(4, 5);
+  if (c4 <= 32) FBBEV_POOL_CASE(4, 8);
+  if (c4 <= 64) FBBEV_POOL_CASE(8, 8);
+  if (c4 <= 128) FBBEV_POOL_CASE(16, 8);
+  FBBEV_POOL_CASE(32, 8);
+#undef FBBEV_POOL_CASE
 }
 
 int split_launch(const float* depth, const float* feat, const int* ranks_depth,
                  const int* ranks_feat, const int* ranks_bev,
-                 const int* interval_starts,
-                 const int* interval_lengths, int n_intervals_max,
-                 int n_points_max, int c, int batch, int64_t zyx, float* out,
-                 void* workspace, cudaStream_t st) {
+                 const int* interval_starts, const int* interval_lengths,
+                 int n_intervals_max, int n_points_max, int c, int batch,
+                 int64_t zyx, float* out, void* workspace, cudaStream_t st) {
   if (reinterpret_cast<uintptr_t>(out) & 15) return FBBEV_ERR_INVALID_ARGUMENT;
   const SplitWs w =
       split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
   const int T = split_pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
   const int64_t n_tiles = (int64_t)batch * tiles_per_b;
-  if (n_intervals_max > 0) {
-    count_launch();
-    const unsigned grid =
-        (unsigned)ceil_div64(w.n_warps_max, kSumThreads / kWarp);
-    const int c4 = c / 4;
-#define FBBEV_SUM_CASE(LGV, VPLV)                                             \
-  interval_sums_kernel<LGV, VPLV><<<grid, kSumThreads, 0, st>>>(              \
-      depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,       \
-      w.warp_first, w.meta, c, w.V, w.X)
-    // group width LG and float4 columns per lane VPL with LG * VPL >= C / 4
-    if (c4 <= 4) FBBEV_SUM_CASE(4, 1);
-    else if (c4 <= 8) FBBEV_SUM_CASE(4, 2);
-    else if (c4 <= 16) FBBEV_SUM_CASE(4, 4);
-    else if (c4 <= 20) FBBEV_SUM_CASE(4, 5);
-    else if (c4 <= 32) FBBEV_SUM_CASE(4, 8);
-    else if (c4 <= 64) FBBEV_SUM_CASE(8, 8);
-    else if (c4 <= 128) FBBEV_SUM_CASE(16, 8);
-    else FBBEV_SUM_CASE(32, 8);
-#undef FBBEV_SUM_CASE
-    int rc = launch_status();
-    if (rc) return rc;
+  // no producers at all when the index is empty (the plan left meta = 0 and
+  // tile_first = 0, so every tile is an empty tile)
+  const int n_sum_ctas = n_intervals_max > 0 ? w.n_sum_ctas : 0;
+  if (n_sum_ctas > 0) {
+    cudaError_t e = cudaMemsetAsync(w.flags, 0, (size_t)n_sum_ctas * 4, st);
+    if (e != cudaSuccess) return (int)e;
   }
   count_launch();
   switch (T) {
     case 128:
-      return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
-                               tiles_per_b, n_tiles, out, st);
+      return launch_pool_t<128>(w, depth, feat, ranks_depth, ranks_feat,
+                                ranks_bev, interval_starts, interval_lengths,
+                                n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
+                                st);
     case 64:
-      return launch_write<64>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, n_tiles, out, st);
+      return launch_pool_t<64>(w, depth, feat, ranks_depth, ranks_feat,
+                               ranks_bev, interval_starts, interval_lengths,
+                               n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
+                               st);
     default:
-      return launch_write<32>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, n_tiles, out, st);
+      return launch_pool_t<32>(w, depth, feat, ranks_depth, ranks_feat,
+                               ranks_bev, interval_starts, interval_lengths,
+                               n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
+                               st);
   }
 }
 
