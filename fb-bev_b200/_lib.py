@@ -42,6 +42,11 @@ _SIGNATURES = {
     "fbbev_voxel_prepare_workspace_bytes": (_sz, [_i64, _i64]),
     "fbbev_voxel_prepare": (
         ctypes.c_int, [_p] + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+    "fbbev_voxel_prepare_cams": (
+        ctypes.c_int, [_p] * 8 + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+    "fbbev_point_sampling": (
+        ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32, _i32] +
+        [ctypes.c_float] * 3 + [_p] * 4),
     "fbbev_msda_fwd": (ctypes.c_int, [_p] * 5 + [_i32] * 7 + [_p, _p]),
     "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
     "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p, _p]),

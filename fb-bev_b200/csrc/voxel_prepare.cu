@@ -39,14 +39,11 @@ __device__ __forceinline__ long long trunc_i64(float f) {
   return static_cast<long long>(f);
 }
 
-__global__ void __launch_bounds__(kPrepThreads) prep_voxelize_kernel(
-    const float* __restrict__ coor, int64_t n_pts, int64_t per_b, GridParams g,
-    int* __restrict__ rank, int* __restrict__ hist) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pts) return;
-  const float x = __ldg(coor + 3 * p + 0);
-  const float y = __ldg(coor + 3 * p + 1);
-  const float z = __ldg(coor + 3 * p + 2);
+__device__ __forceinline__ void voxelize_point(float x, float y, float z,
+                                               int64_t p, int64_t per_b,
+                                               const GridParams& g,
+                                               int* __restrict__ rank,
+                                               int* __restrict__ hist) {
   // __fsub_rn / __fdiv_rn: IEEE round-to-nearest, never contracted or
   // replaced by a reciprocal multiply
   const long long cx = trunc_i64(__fdiv_rn(__fsub_rn(x, g.lo[0]), g.iv[0]));
@@ -62,6 +59,74 @@ __global__ void __launch_bounds__(kPrepThreads) prep_voxelize_kernel(
     atomicAdd(hist + r, 1);
   }
   rank[p] = r;
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_voxelize_kernel(
+    const float* __restrict__ coor, int64_t n_pts, int64_t per_b, GridParams g,
+    int* __restrict__ rank, int* __restrict__ hist) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  voxelize_point(__ldg(coor + 3 * p + 0), __ldg(coor + 3 * p + 1),
+                 __ldg(coor + 3 * p + 2), p, per_b, g, rank, hist);
+}
+
+// Same, but the ego-frame coordinate of point (b, n, d, h, w) is evaluated here
+// from the camera matrices instead of being read from a materialised
+// (B,N,D,H,W,3) tensor: get_lidar_coor (view_transformer.py:458-498) fused into
+// the voxelisation.  The chain is the reference's --
+//   p = frustum - post_trans;  p = inv(post_rots) p;  p = (p.x p.z, p.y p.z, p.z);
+//   p = (rots inv(K)) p + trans;  p = bda p
+// -- in fp32 with one FMA per term.  torch evaluates the same chain through
+// cuBLAS batched products whose internal rounding is library- and
+// device-dependent, so the two agree to fp32 rounding, not bit for bit.
+struct CamGeom {
+  const float* us;      // [W]  frustum u (linspace over the input width)
+  const float* vs;      // [H]  frustum v
+  const float* ds;      // [D]  frustum depth bins
+  const float* ipr;     // [B*N][9] inverse(post_rots)
+  const float* ptr;     // [B*N][3] post_trans
+  const float* comb;    // [B*N][9] rots @ inverse(intrins)
+  const float* trn;     // [B*N][3] trans
+  const float* bda;     // [B][9]
+  int N, D, H, W;
+};
+
+__device__ __forceinline__ void mat3_apply(const float* __restrict__ m, float x,
+                                           float y, float z, float& ox,
+                                           float& oy, float& oz) {
+  ox = fmaf(m[2], z, fmaf(m[1], y, m[0] * x));
+  oy = fmaf(m[5], z, fmaf(m[4], y, m[3] * x));
+  oz = fmaf(m[8], z, fmaf(m[7], y, m[6] * x));
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_voxelize_cams_kernel(
+    CamGeom cg, int64_t n_pts, int64_t per_b, GridParams g,
+    int* __restrict__ rank, int* __restrict__ hist) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  const int w = (int)(p % cg.W);
+  int64_t t = p / cg.W;
+  const int h = (int)(t % cg.H);
+  t /= cg.H;
+  const int d = (int)(t % cg.D);
+  const int64_t bn = t / cg.D;
+  const int64_t b = bn / cg.N;
+  const float* pt = cg.ptr + bn * 3;
+  float x = __fsub_rn(__ldg(cg.us + w), __ldg(pt + 0));
+  float y = __fsub_rn(__ldg(cg.vs + h), __ldg(pt + 1));
+  float z = __fsub_rn(__ldg(cg.ds + d), __ldg(pt + 2));
+  float a, bb, c;
+  mat3_apply(cg.ipr + bn * 9, x, y, z, a, bb, c);
+  x = __fmul_rn(a, c);
+  y = __fmul_rn(bb, c);
+  z = c;
+  mat3_apply(cg.comb + bn * 9, x, y, z, a, bb, c);
+  const float* tr = cg.trn + bn * 3;
+  a = __fadd_rn(a, __ldg(tr + 0));
+  bb = __fadd_rn(bb, __ldg(tr + 1));
+  c = __fadd_rn(c, __ldg(tr + 2));
+  mat3_apply(cg.bda + b * 9, a, bb, c, x, y, z);
+  voxelize_point(x, y, z, p, per_b, g, rank, hist);
 }
 
 // ----- two-quantity exclusive scan over hist: (points, occupied voxels) -----
@@ -256,17 +321,19 @@ FBBEV_API size_t fbbev_voxel_prepare_workspace_bytes(int64_t n_points,
   return prep_layout(n_points, n_voxels_total, nullptr, nullptr);
 }
 
-FBBEV_API int fbbev_voxel_prepare(
-    const float* coor, int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
-    const float* lo_host, const float* iv_host, const float* gs_host,
-    int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
-    int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts,
-    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
+// coor != NULL: voxelise the given coordinates; else evaluate them from *cg.
+static int voxel_prepare_impl(
+    const float* coor, const CamGeom* cg, int32_t B, int32_t N, int32_t D,
+    int32_t H, int32_t W, const float* lo_host, const float* iv_host,
+    const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
+    int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
+    int32_t* counts, void* workspace, size_t workspace_bytes,
+    fbbev_stream_t stream) {
   if (B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || !lo_host || !iv_host ||
       !gs_host)
     return FBBEV_ERR_INVALID_ARGUMENT;
-  if (!coor || !ranks_bev || !ranks_depth || !ranks_feat || !interval_starts ||
-      !interval_lengths || !counts || !workspace)
+  if ((!coor && !cg) || !ranks_bev || !ranks_depth || !ranks_feat ||
+      !interval_starts || !interval_lengths || !counts || !workspace)
     return FBBEV_ERR_INVALID_ARGUMENT;
   GridParams g;
   for (int k = 0; k < 3; ++k) {
@@ -293,8 +360,12 @@ FBBEV_API int fbbev_voxel_prepare(
   const unsigned pt_grid = (unsigned)ceil_div64(n_pts, kPrepThreads);
   const int n_scan_blocks = (int)ceil_div64(n_vox, kScanTile);
   count_launch(6);
-  prep_voxelize_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
-      coor, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
+  if (coor)
+    prep_voxelize_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
+        coor, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
+  else
+    prep_voxelize_cams_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
+        *cg, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
   prep_scan_reduce_kernel<<<n_scan_blocks, kPrepThreads, 0, st>>>(
       w.hist, n_vox, w.block_sums);
   prep_scan_spine_kernel<<<1, kPrepThreads, 0, st>>>(w.block_sums,
@@ -308,4 +379,40 @@ FBBEV_API int fbbev_voxel_prepare(
       w.bucket, w.rank, w.offset, w.hist, counts, D, (int64_t)H * W, ranks_bev,
       ranks_depth, ranks_feat);
   return launch_status();
+}
+
+FBBEV_API int fbbev_voxel_prepare(
+    const float* coor, int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+    const float* lo_host, const float* iv_host, const float* gs_host,
+    int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+    int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts,
+    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
+  if (!coor) return FBBEV_ERR_INVALID_ARGUMENT;
+  return voxel_prepare_impl(coor, nullptr, B, N, D, H, W, lo_host, iv_host,
+                            gs_host, ranks_bev, ranks_depth, ranks_feat,
+                            interval_starts, interval_lengths, counts,
+                            workspace, workspace_bytes, stream);
+}
+
+FBBEV_API int fbbev_voxel_prepare_cams(
+    const float* frustum_u, const float* frustum_v, const float* frustum_d,
+    const float* inv_post_rots, const float* post_trans, const float* cam2ego,
+    const float* trans, const float* bda, int32_t B, int32_t N, int32_t D,
+    int32_t H, int32_t W, const float* lo_host, const float* iv_host,
+    const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
+    int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
+    int32_t* counts, void* workspace, size_t workspace_bytes,
+    fbbev_stream_t stream) {
+  if (!frustum_u || !frustum_v || !frustum_d || !inv_post_rots ||
+      !post_trans || !cam2ego || !trans || !bda)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  CamGeom cg;
+  cg.us = frustum_u; cg.vs = frustum_v; cg.ds = frustum_d;
+  cg.ipr = inv_post_rots; cg.ptr = post_trans; cg.comb = cam2ego;
+  cg.trn = trans; cg.bda = bda;
+  cg.N = N; cg.D = D; cg.H = H; cg.W = W;
+  return voxel_prepare_impl(nullptr, &cg, B, N, D, H, W, lo_host, iv_host,
+                            gs_host, ranks_bev, ranks_depth, ranks_feat,
+                            interval_starts, interval_lengths, counts,
+                            workspace, workspace_bytes, stream);
 }

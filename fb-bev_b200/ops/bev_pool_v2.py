@@ -18,7 +18,8 @@ import torch
 from .. import _lib
 
 __all__ = ['bev_pool_v2', 'bev_pool_v2_dense', 'QuickCumsumCuda',
-           'voxel_pooling_prepare_v2', 'VoxelIndex']
+           'voxel_pooling_prepare_v2', 'voxel_pooling_prepare_from_cams',
+           'VoxelIndex']
 
 
 def _feat_intervals(ranks_feat, ranks_depth, ranks_bev):
@@ -274,4 +275,47 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
             _lib.ptr(idx[2]), _lib.ptr(idx[3]), _lib.ptr(idx[4]),
             _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_voxel_prepare')
+    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts)
+
+
+def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
+                                    cam2ego, trans, bda, depth_bins,
+                                    grid_lower_bound, grid_interval,
+                                    grid_size):
+    """``get_lidar_coor`` + ``voxel_pooling_prepare_v2`` in one pass
+    (view_transformer.py:458-498, 547-605): the (B,N,D,H,W,3) coordinate
+    tensor is never materialised (``fbbev_voxel_prepare_cams``).
+
+    frustum_axes = (u [W], v [H], d [D]) CUDA float tensors;
+    inv_post_rots / cam2ego (B,N,3,3); post_trans / trans (B,N,3); bda (B,3,3).
+    Returns a :class:`VoxelIndex`.  Agrees with the two-step route to fp32
+    rounding of the coordinates (see include/fbbev_b200.h)."""
+    fu, fv, fd = (t.contiguous().float() for t in frustum_axes)
+    dev = _lib.require_cuda(fu, fv, fd, inv_post_rots, post_trans, cam2ego,
+                            trans, bda)
+    mats = [t.contiguous().float() for t in
+            (inv_post_rots, post_trans, cam2ego, trans, bda)]
+    B, N = mats[0].shape[:2]
+    D, H, W = fd.shape[0], fv.shape[0], fu.shape[0]
+    assert D == depth_bins
+    lo = [float(v) for v in torch.as_tensor(grid_lower_bound).float().cpu()]
+    iv = [float(v) for v in torch.as_tensor(grid_interval).float().cpu()]
+    gs = [float(v) for v in torch.as_tensor(grid_size).float().cpu()]
+    n_pts = B * N * D * H * W
+    n_vox = B * int(gs[0]) * int(gs[1]) * int(gs[2])
+    L = _lib.lib()
+    idx = torch.empty((5, n_pts), dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.fbbev_voxel_prepare_cams(
+            _lib.ptr(fu), _lib.ptr(fv), _lib.ptr(fd), _lib.ptr(mats[0]),
+            _lib.ptr(mats[1]), _lib.ptr(mats[2]), _lib.ptr(mats[3]),
+            _lib.ptr(mats[4]), B, N, D, H, W, _lib.c_floats(lo),
+            _lib.c_floats(iv), _lib.c_floats(gs), _lib.ptr(idx[0]),
+            _lib.ptr(idx[1]), _lib.ptr(idx[2]), _lib.ptr(idx[3]),
+            _lib.ptr(idx[4]), _lib.ptr(counts), _lib.ptr(ws), ws_bytes,
+            _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_voxel_prepare_cams')
     return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts)

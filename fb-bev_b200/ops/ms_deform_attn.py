@@ -19,7 +19,8 @@ from .. import _lib
 
 __all__ = ['MultiScaleDeformableAttnFunction_fp32',
            'MultiScaleDeformableAttnFunction_fp16', 'ms_deform_attn_forward',
-           'ms_deform_attn_fused', 'da_spatial_cross_attention_core']
+           'ms_deform_attn_fused', 'da_spatial_cross_attention_core',
+           'point_sampling']
 
 
 def _i64(t, dev):
@@ -166,3 +167,34 @@ def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
             _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_da_sca_fwd')
     return out
+
+
+def point_sampling(axes, inv_bda, trans, ego2cam, post_rots, post_trans,
+                   input_size, eps=1e-5):
+    """One-kernel ``bevformer_encoder.point_sampling``
+    (bevformer_encoder.py:92-120), ``fbbev_point_sampling``.
+
+    axes = (X [nX], Y [nY], Z [nZ]) voxel-centre coordinates; inv_bda (B,3,3);
+    ego2cam / post_rots (B,N,3,3); trans / post_trans (B,N,3);
+    input_size = (H_in, W_in).  Returns ``(reference_points_cam (N,B,nq,Z,2),
+    mask (N,B,nq,Z) bool, depth (N,B,nq,Z,1))`` with nq = nY*nX."""
+    X, Y, Z = (t.contiguous().float() for t in axes)
+    dev = _lib.require_cuda(X, Y, Z, inv_bda, trans, ego2cam, post_rots,
+                            post_trans)
+    mats = [t.contiguous().float() for t in
+            (inv_bda, trans, ego2cam, post_rots, post_trans)]
+    B, N = mats[1].shape[:2]
+    nX, nY, nZ = X.shape[0], Y.shape[0], Z.shape[0]
+    nq = nX * nY
+    ref = torch.empty((N, B, nq, nZ, 2), dtype=torch.float32, device=dev)
+    dep = torch.empty((N, B, nq, nZ, 1), dtype=torch.float32, device=dev)
+    msk = torch.empty((N, B, nq, nZ), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fbbev_point_sampling(
+            _lib.ptr(X), _lib.ptr(Y), _lib.ptr(Z), nX, nY, nZ,
+            _lib.ptr(mats[0]), _lib.ptr(mats[1]), _lib.ptr(mats[2]),
+            _lib.ptr(mats[3]), _lib.ptr(mats[4]), B, N, float(input_size[1]),
+            float(input_size[0]), float(eps), _lib.ptr(ref), _lib.ptr(dep),
+            _lib.ptr(msk), _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_point_sampling')
+    return ref, msk.view(torch.bool), dep

@@ -22,7 +22,10 @@ coordinates it starts from are rounded identically.
 import torch
 import torch.nn as nn
 
+import os
+
 from ..ops.bev_pool_v2 import (VoxelIndex, bev_pool_v2, bev_pool_v2_dense,
+                               voxel_pooling_prepare_from_cams,
                                voxel_pooling_prepare_v2)
 from ..registry import BaseModule, register
 
@@ -41,7 +44,20 @@ def gen_dx_bx(xbound, ybound, zbound):
 
 
 class _LSSBase(BaseModule):
-    """Shared geometry / index machinery of the 2-D and 3-D transformers."""
+    """Shared geometry / index machinery of the 2-D and 3-D transformers.
+
+    ``fused_geometry`` (class attribute, default True; env
+    ``FBBEV_EXACT_GEOMETRY=1`` or setting the attribute to False turns it off):
+    ``forward`` evaluates the frustum -> ego chain inside the voxelisation
+    kernel instead of materialising ``get_lidar_coor``'s (B,N,D,H,W,3) tensor
+    through eager PyTorch (1.0 ms of cuBLAS batched 3x3 products for 338k points
+    on B200 -- 15x the pooling kernel).  Both routes implement the same fp32
+    chain; they differ only in the rounding order inside the 3x3 products, which
+    cuBLAS does not specify either.  ``get_lidar_coor`` and
+    ``voxel_pooling_prepare_v2(coor)`` keep the reference's exact contract.
+    """
+
+    fused_geometry = os.environ.get('FBBEV_EXACT_GEOMETRY', '0') != '1'
 
     def __init__(self, grid_config, input_size, downsample, accelerate,
                  uniform, with_cp):
@@ -107,6 +123,29 @@ class _LSSBase(BaseModule):
         pts = bda.view(B, 1, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1)).squeeze(-1)
         return pts
 
+    def _frustum_axes(self, device):
+        key = str(device)
+        cache = self.__dict__.setdefault('_axes_cache', {})
+        if key not in cache:
+            f = self.frustum
+            cache[key] = (f[0, 0, :, 0].contiguous().to(device),
+                          f[0, :, 0, 1].contiguous().to(device),
+                          f[:, 0, 0, 2].contiguous().to(device))
+        return cache[key]
+
+    def prepare_index_from_cams(self, rots, trans, cam2imgs, post_rots,
+                                post_trans, bda):
+        """Index straight from the camera parameters (fused geometry).  The
+        two 3x3 products the reference forms before touching the points
+        (view_transformer.py:483-491) are formed here by the same torch ops
+        (inv_ex == torch.inverse without the host-side error check)."""
+        inv_pr = torch.linalg.inv_ex(post_rots)[0]
+        cam2ego = rots.matmul(torch.linalg.inv_ex(cam2imgs)[0])
+        return voxel_pooling_prepare_from_cams(
+            self._frustum_axes(rots.device), inv_pr, post_trans, cam2ego,
+            trans, bda, self.D, self.grid_lower_bound, self.grid_interval,
+            self.grid_size)
+
     # -- view_transformer.py:547-605 ------------------------------------
     def prepare_index(self, coor):
         """Device-resident index of ``coor`` (no host sync)."""
@@ -123,7 +162,7 @@ class _LSSBase(BaseModule):
 
     # -- view_transformer.py:500-519 ------------------------------------
     def init_acceleration_v2(self, coor):
-        idx = self.prepare_index(coor)
+        idx = coor if isinstance(coor, VoxelIndex) else self.prepare_index(coor)
         self._index = idx
         rb, rd, rf, st, ln = idx.trimmed()
         self.ranks_bev, self.ranks_depth, self.ranks_feat = rb, rd, rf
@@ -131,8 +170,11 @@ class _LSSBase(BaseModule):
 
     def pre_compute(self, cam_params):
         if self.initial_flag:
-            coor = self.get_lidar_coor(*cam_params)
-            self.init_acceleration_v2(coor)
+            if self.fused_geometry:
+                self.init_acceleration_v2(
+                    self.prepare_index_from_cams(*cam_params))
+            else:
+                self.init_acceleration_v2(self.get_lidar_coor(*cam_params))
             self.initial_flag = False
 
     def _bev_feat_shape(self, depth, feat_nhwc):
@@ -195,6 +237,9 @@ class LSSViewTransformerFunction3D(_LSSBase):
         if self.accelerate:
             bev_feat = self._pool(self._index, depth, tran_feat)
             return bev_feat.permute(0, 1, 3, 4, 2)
+        if self.fused_geometry:
+            idx = self.prepare_index_from_cams(*cam_params)
+            return self._pool(idx, depth, tran_feat).permute(0, 1, 3, 4, 2)
         coor = self.get_lidar_coor(*cam_params)
         return self.voxel_pooling_v2(coor, depth, tran_feat)
 
@@ -237,6 +282,9 @@ class LSSViewTransformerFunction(_LSSBase):
         if self.accelerate:
             # the reference squeezes Z here (:283): 4-D only when Z == 1
             return self._pool(self._index, depth, tran_feat).squeeze(2)
+        if self.fused_geometry:
+            idx = self.prepare_index_from_cams(*cam_params)
+            return self._collapse(self._pool(idx, depth, tran_feat))
         coor = self.get_lidar_coor(*cam_params)
         return self.voxel_pooling_v2(coor, depth, tran_feat)
 

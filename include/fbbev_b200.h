@@ -173,9 +173,50 @@ int fbbev_voxel_prepare(const float* coor, int32_t B, int32_t N, int32_t D,
                         void* workspace, size_t workspace_bytes,
                         fbbev_stream_t stream);
 
+/*
+ * voxel_pooling_prepare_v2 with get_lidar_coor fused in
+ *   (view_transformer.py:458-498 + 547-605): the (B,N,D,H,W,3) coordinate tensor
+ *   is never materialised.  frustum_u [W], frustum_v [H], frustum_d [D] are the
+ *   three axes of the frustum template (create_frustum, :389-411);
+ *   inv_post_rots = inverse(post_rots) (B*N,3,3); cam2ego = rots @ inverse(K)
+ *   (B*N,3,3) -- the two tiny products the reference also forms before touching
+ *   the points (:483-491); post_trans, trans (B*N,3); bda (B,3,3).
+ * The per-point chain is evaluated in fp32 with one FMA per term; the reference
+ * evaluates it through cuBLAS batched products with unspecified rounding order,
+ * so a point within one fp32 ulp of a voxel face may be binned in the
+ * neighbouring voxel.  fbbev_voxel_prepare on get_lidar_coor's own output is
+ * the bit-exact route.
+ */
+int fbbev_voxel_prepare_cams(
+    const float* frustum_u, const float* frustum_v, const float* frustum_d,
+    const float* inv_post_rots, const float* post_trans, const float* cam2ego,
+    const float* trans, const float* bda, int32_t B, int32_t N, int32_t D,
+    int32_t H, int32_t W, const float* lo_host, const float* iv_host,
+    const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
+    int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
+    int32_t* counts, void* workspace, size_t workspace_bytes,
+    fbbev_stream_t stream);
+
 /* =====================================================================
  * B -- BEV -> image depth-aware spatial cross-attention (MSDeformAttn)
  * ===================================================================== */
+
+/*
+ * One-kernel `bevformer_encoder.point_sampling`
+ *   .../backward_projection/bevformer_utils/bevformer_encoder.py:92-120.
+ * X [nX], Y [nY], Z [nZ]: voxel-centre coordinates per axis (get_reference_points
+ * '3d', :64-70); inv_bda = inverse(bda) (B,3,3); ego2cam = inverse(rots @
+ * inverse(K)) (B*N,3,3); trans, post_trans (B*N,3); post_rots (B*N,3,3);
+ * (w_in, h_in) = data_config input_size; eps = 1e-5.
+ * Outputs in the reference's layouts: ref_cam (N,B,nY*nX,nZ,2), depth
+ * (N,B,nY*nX,nZ), mask (N,B,nY*nX,nZ) uint8.
+ */
+int fbbev_point_sampling(
+    const float* X, const float* Y, const float* Z, int32_t nX, int32_t nY,
+    int32_t nZ, const float* inv_bda, const float* trans, const float* ego2cam,
+    const float* post_rots, const float* post_trans, int32_t B, int32_t N,
+    float w_in, float h_in, float eps, float* ref_cam, float* depth,
+    uint8_t* mask, fbbev_stream_t stream);
 
 /*
  * Drop-in for `ext_module.ms_deform_attn_forward` (mmcv-full 1.5.2 `_ext`)

@@ -161,3 +161,30 @@ def test_backward_projection_vs_reference_golden(case):
     vis = g["per_cam_mask"]
     np.testing.assert_allclose(ref_cam.cpu().numpy()[vis],
                                g["reference_points_cam"][vis], atol=1e-4)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_point_sampling_vs_torch_and_golden(case):
+    """fbbev_point_sampling (the encoder's default) against the eager-PyTorch
+    chain and the reference's recorded tensors."""
+    g, bp = build_bp(case, DEV)
+    enc = bp.transformer.encoder
+    cams = cam_params(g, DEV)
+    ref_cam, mask, depth = enc.point_sampling_fused(cams)
+    ref_3d = enc.get_reference_points(int(g["bev_h"]), int(g["bev_w"]),
+                                      dim='3d', device=DEV)
+    _, ref_cam_t, mask_t, depth_t = enc.point_sampling(ref_3d, enc.pc_range,
+                                                       None, cam_params=cams)
+    assert ref_cam.shape == ref_cam_t.shape and depth.shape == depth_t.shape
+    assert mask.dtype == torch.bool and mask.shape == mask_t.shape
+    assert (mask == mask_t).float().mean().item() >= 0.9999
+    both = (mask & mask_t).cpu().numpy()
+    np.testing.assert_allclose(ref_cam.cpu().numpy()[both],
+                               ref_cam_t.cpu().numpy()[both], atol=2e-5)
+    np.testing.assert_allclose(depth.cpu().numpy()[both],
+                               depth_t.cpu().numpy()[both], rtol=1e-5,
+                               atol=1e-4)
+    assert (mask.cpu().numpy() == g["per_cam_mask"]).mean() >= 0.999
+    vis = g["per_cam_mask"] & mask.cpu().numpy()
+    np.testing.assert_allclose(ref_cam.cpu().numpy()[vis],
+                               g["reference_points_cam"][vis], atol=1e-4)

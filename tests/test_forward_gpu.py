@@ -163,6 +163,7 @@ def test_dense_pool_vs_oracle(oracle_cpu, name, batch):
     # as two partials, so the two kernels agree to rounding, not bit for bit)
     assert (ref_layout.permute(0, 4, 1, 2, 3) - got).abs().max().item() <= ATOL
     # sync-free plugin path (padded buffers + device counts) == trimmed path
+    vt.fused_geometry = False          # same coordinates as `coor` above
     bev = vt(cam, feat, depth)
     assert torch.equal(bev, got.permute(0, 1, 3, 4, 2))
 
@@ -305,3 +306,31 @@ def test_wide_channels(oracle_cpu):
     ref_layout = QuickCumsumCuda.apply(*args, shape, st.to(DEV),
                                        ln.int().to(DEV))
     assert (ref_layout.permute(0, 4, 1, 2, 3) - got).abs().max().item() <= ATOL
+
+
+@pytest.mark.parametrize("name,batch", [("shipped", 2), ("fbocc_200", 1),
+                                        ("unit_128", 1)])
+def test_fused_geometry_vs_torch_geometry(name, batch):
+    """get_lidar_coor fused into the voxelisation kernel (the plugin's default
+    forward) against the eager-PyTorch chain: same fp32 formula, only the
+    rounding order inside the 3x3 products may differ, so at most a handful of
+    points that sit within an ulp of a voxel face change voxel."""
+    vt, cam, depth, feat = make_case(name, batch)
+    exact = vt.prepare_index(vt.get_lidar_coor(*cam))
+    fused = vt.prepare_index_from_cams(*cam)
+    ne, nf = exact.counts.tolist(), fused.counts.tolist()
+    n_pts = exact.ranks_bev.numel()
+    # voxel of every point (-1 = dropped) under both routes
+    def per_point(idx, n_kept):
+        v = torch.full((n_pts,), -1, dtype=torch.int32, device=DEV)
+        v[idx.ranks_depth[:n_kept].long()] = idx.ranks_bev[:n_kept]
+        return v
+    ve, vf = per_point(exact, ne[0]), per_point(fused, nf[0])
+    flips = int((ve != vf).sum())
+    assert flips <= max(2, n_pts // 50000), (flips, n_pts)
+    vt.fused_geometry = True
+    bev_f = vt(cam, feat, depth)
+    vt.fused_geometry = False
+    bev_e = vt(cam, feat, depth)
+    bad = int(((bev_f - bev_e).abs() > ATOL).any(1).sum())  # voxels touched
+    assert bad <= 2 * flips, (bad, flips)
