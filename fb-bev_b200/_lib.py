@@ -11,7 +11,9 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfbbev_b200.so")
+# FBBEV_LIB: kernel-tuning aid (tools/), points at a variant build of the same ABI
+LIB_PATH = os.environ.get("FBBEV_LIB") or os.path.join(
+    _HERE, "lib", "libfbbev_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 _p = ctypes.c_void_p

@@ -9,30 +9,27 @@
 //    ~55 % busy (37-51 M warp instructions) and long-scoreboard / barrier stalls:
 //    index chasing (tile table -> index words -> depth / feat rows) inside the
 //    CTA that owns the 40 KB output tile starves the store stream.
-// So the index chasing is moved out of the CTA that owns an output tile, and
-// both kinds of work run in ONE launch as producer / consumer CTAs:
+// So the index chasing is moved out of the CTA that owns an output tile:
 //
-//  producers (blockIdx < n_sum_ctas) -- "interval sums": warp w folds the 32
-//      kept points [32w, 32w+32) -- perfectly balanced, so the dense voxels next
-//      to a camera (up to 63 points on the 200x200x16 grid, thousands on the
-//      1-camera 128x128 grid: the reference kernel's and every tile-owning
-//      kernel's tail) are spread over many warps.  Coalesced index loads; every
-//      run of equal voxel rank is folded by a 4-lane group (8 runs per warp
-//      instruction) with 128-bit feat loads and one FMA per point and channel
-//      in point order (bev_pool_cuda.cu:36-40).  Interval sums go to compact
-//      rows V[interval][C] (43 MB for the 200x200x16 grid; they never leave
-//      L2), the part of an interval that spills into later slices to carry rows
-//      X[slice][C].  A producer CTA publishes a flag when its rows are written.
-//  consumers (the other CTAs) -- "dense write": a CTA owns T consecutive voxel
-//      ranks x all C channels.  Empty tiles stream zeros at once; the others
-//      wait for the flags of the (one or two) producers that cover their
-//      points, copy the rows of their contiguous intervals V[i0:i1] into shared
-//      memory with cp.async, add carry rows in slice order, and stream the tile
-//      out channel row by channel row with 128-bit evict-first stores.
-//  Producers have the lowest block indices, so they are resident before any
-//  consumer can wait on them; consumers never block producers.
+//  K1 "interval sums": warp w folds the 32 kept points [32w, 32w+32) --
+//      perfectly balanced, so the dense voxels next to a camera (up to 63
+//      points on the 200x200x16 grid, thousands on the 1-camera 128x128 grid:
+//      the reference kernel's and every tile-owning kernel's tail) are spread
+//      over many warps.  Coalesced index loads; a 4-lane group owns 4
+//      consecutive points (128-bit feat loads that depend only on the index
+//      words, one FMA per point and channel in point order,
+//      bev_pool_cuda.cu:36-40) and runs of equal voxel rank are stitched
+//      across groups through shared memory.  Interval sums go to compact rows
+//      V[interval][C] (43 MB for the 200x200x16 grid; they stay in L2), the
+//      part of an interval that spills into later slices to carry rows
+//      X[slice][C].
+//  K2 "dense write": a CTA owns T consecutive voxel ranks x all C channels.
+//      Empty tiles stream zeros at once; the others copy the rows of their
+//      contiguous intervals V[i0:i1] into shared memory with cp.async, add
+//      carry rows in slice order, and stream the tile out channel row by channel
+//      row with 128-bit evict-first stores.
 //  Every output element and every V / X row is written exactly once; no
-//  floating-point atomics; results are deterministic.
+//  atomics; results are deterministic.
 //
 // Requires C % 4 == 0 and (Z*Y*X) % 4 == 0, 16-byte aligned out.
 #include <algorithm>
@@ -42,10 +39,14 @@
 
 namespace fbbev {
 
-constexpr int kPoolThreads = 256;  // both roles
-constexpr int kSumThreads = kPoolThreads;
-constexpr int kWrThreads = kPoolThreads;
-constexpr int kWrWarps = kWrThreads / kWarp;
+constexpr int kPoolThreads = 256;  // dense-write CTAs
+#ifndef FBBEV_SUM_THREADS
+#define FBBEV_SUM_THREADS 128
+#endif
+#ifndef FBBEV_SUM_MINB
+#define FBBEV_SUM_MINB 6
+#endif
+constexpr int kSumThreads = FBBEV_SUM_THREADS;  // interval-sum CTAs
 
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
@@ -125,28 +126,34 @@ __global__ void split_plan_kernel(
 // the dense voxels next to a camera (up to 63 points each on the 200x200x16
 // grid, thousands on the 1-camera 128x128 grid) are spread over many warps.
 // Two dependent loads reach the data (plan table -> index words, coalesced).
-// Inside the slice every run of equal voxel rank (a segment == an interval or
-// a piece of one) is folded by an LG-lane group -- 8 segments per warp
-// instruction for LG = 4 -- with 128-bit feat loads and one FMA per point and
-// channel in point order (the reference's order, bev_pool_cuda.cu:36-40).
-// An interval that STARTS in the slice is stored to its row V[interval]; the
-// leading part of an interval that started in an earlier slice goes to the
-// slice's carry row X[w] and is added, in slice order, by K2.  Every row is
-// written exactly once; no atomics; deterministic.
+// An LG-lane group owns LG CONSECUTIVE points of the slice, whatever the run
+// structure: its 128-bit feat loads (VPL per lane and point) depend only on the
+// index words, so two points per lane are in flight and the load chain does not
+// grow with the run lengths.  The group folds its points in point order (one
+// FMA per point and channel, bev_pool_cuda.cu:36-40); a run of equal voxel rank
+// that ends inside the group is flushed at once, a run that crosses into the
+// following groups collects their leading partial sums ("heads") through shared
+// memory, in point order.
+// A run that STARTS in the slice is stored to its row V[interval]; the leading
+// part of an interval that started in an earlier slice goes to the slice's
+// carry row X[w] and is added, in slice order, by K2.  Every row is written
+// exactly once; no atomics; deterministic.
 template <int LG, int VPL>
-__device__ __forceinline__ void interval_sums_role(
-    int cta, const float* __restrict__ depth, const float* __restrict__ feat,
-    const int* __restrict__ ranks_depth, const int* __restrict__ ranks_feat,
-    const int* __restrict__ ranks_bev, const int* __restrict__ interval_starts,
-    const int* __restrict__ warp_first, const int* __restrict__ meta, int c,
-    float* __restrict__ V, float* __restrict__ X) {
+__global__ void __launch_bounds__(kSumThreads, FBBEV_SUM_MINB)
+    interval_sums_kernel(const float* __restrict__ depth,
+                         const float* __restrict__ feat,
+                         const int* __restrict__ ranks_depth,
+                         const int* __restrict__ ranks_feat,
+                         const int* __restrict__ ranks_bev,
+                         const int* __restrict__ interval_starts,
+                         const int* __restrict__ warp_first,
+                         const int* __restrict__ meta, int c,
+                         float* __restrict__ V, float* __restrict__ X) {
   constexpr int WPC = kSumThreads / kWarp;
-  constexpr int GPW = kWarp / LG;  // segments folded per warp instruction
-  __shared__ int s_k0[WPC][kPtsPerWarp + 1];
-  __shared__ int s_rf[WPC][kPtsPerWarp];
-  __shared__ float s_d[WPC][kPtsPerWarp];
+  constexpr int GPW = kWarp / LG;  // groups per warp
+  __shared__ float4 s_head[WPC][GPW][LG * VPL];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int64_t w = (int64_t)cta * WPC + wi;
+  const int64_t w = (int64_t)blockIdx.x * WPC + wi;
   if (w >= meta[2]) return;
   const int n = meta[0];
   const int base = (int)w * kPtsPerWarp;
@@ -162,122 +169,165 @@ __device__ __forceinline__ void interval_sums_role(
   // does the slice begin inside an interval that started earlier?
   const int carry = !(lb < n && __ldg(interval_starts + lb) == base);
   const int prev = __shfl_up_sync(kFull, rbL, 1);
-  const bool is_start = lane < cnt && (lane == 0 || rbL != prev);
-  const unsigned starts = __ballot_sync(kFull, is_start);
-  const int nseg = __popc(starts);
-  s_rf[wi][lane] = rfL;
-  s_d[wi][lane] = dL;
-  if (is_start) s_k0[wi][__popc(starts & ((1u << lane) - 1u))] = lane;
-  if (lane == 0) s_k0[wi][nseg] = cnt;
-  __syncwarp();
+  const unsigned starts =
+      __ballot_sync(kFull, lane < cnt && (lane == 0 || rbL != prev));
 
-  const int gl = lane % LG, g = lane / LG;
+  const int gl = lane % LG, g = lane / LG, p0 = g * LG;
   const int c4 = c >> 2;
-  const float4* feat4 = reinterpret_cast<const float4*>(feat);
-  for (int j = g; j < nseg; j += GPW) {
-    const int k0 = s_k0[wi][j], k1 = s_k0[wi][j + 1];
-    float4 acc[VPL];
+  const float4* feat4 = reinterpret_cast<const float4*>(feat) + gl;
+  float4* V4 = reinterpret_cast<float4*>(V) + gl;
+  float4* X4 = reinterpret_cast<float4*>(X) + gl;
+  float4* hd = &s_head[wi][g][gl];
+
+  float4 acc[VPL];
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = k0; k < k1; ++k) {
-      const float d = s_d[wi][k];
-      const float4* f = feat4 + (int64_t)s_rf[wi][k] * c4;
-#pragma unroll
-      for (int q = 0; q < VPL; ++q) {
-        const int vi = gl + LG * q;
-        if (vi < c4) {
-          const float4 x = __ldg(f + vi);
-          acc[q].x = fmaf(x.x, d, acc[q].x);
-          acc[q].y = fmaf(x.y, d, acc[q].y);
-          acc[q].z = fmaf(x.z, d, acc[q].z);
-          acc[q].w = fmaf(x.w, d, acc[q].w);
-        }
-      }
+  for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool head = !((starts >> p0) & 1u);  // the group opens inside a run
+  int cur = p0;                        // first point of the run being folded
+
+  // store the finished run: a head goes to shared memory, a run that started
+  // in this group to its own row
+  auto flush = [&]() {
+    float4* dst;
+    if (head) {
+      dst = hd;
+    } else {
+      const int j = __popc(starts & ((1u << cur) - 1u));
+      dst = (j == 0 && carry) ? X4 + w * c4
+                              : V4 + (int64_t)(lb + j - carry) * c4;
     }
-    float4* dst = (j == 0 && carry)
-                      ? reinterpret_cast<float4*>(X) + w * c4
-                      : reinterpret_cast<float4*>(V) +
-                            (int64_t)(lb + j - carry) * c4;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q)
+      if (head || gl + LG * q < c4) dst[LG * q] = acc[q];
+  };
+
+#pragma unroll
+  for (int k = 0; k < LG; k += 2) {
+    const int pa = p0 + k, pb = pa + 1;
+    const int rfa = __shfl_sync(kFull, rfL, pa), rfb = __shfl_sync(kFull, rfL, pb);
+    const float da = __shfl_sync(kFull, dL, pa), db = __shfl_sync(kFull, dL, pb);
+    float4 xa[VPL], xb[VPL];
+    const float4* fa = feat4 + (int64_t)rfa * c4;
+    const float4* fb = feat4 + (int64_t)rfb * c4;
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
-      const int vi = gl + LG * q;
-      if (vi < c4) dst[vi] = acc[q];
+      const bool col = gl + LG * q < c4;
+      xa[q] = (col && pa < cnt) ? __ldg(fa + LG * q)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[q] = (col && pb < cnt) ? __ldg(fb + LG * q)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (pa < cnt) {
+      if (k > 0 && ((starts >> pa) & 1u)) {
+        flush();
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        head = false;
+        cur = pa;
+      }
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        acc[q].x = fmaf(xa[q].x, da, acc[q].x);
+        acc[q].y = fmaf(xa[q].y, da, acc[q].y);
+        acc[q].z = fmaf(xa[q].z, da, acc[q].z);
+        acc[q].w = fmaf(xa[q].w, da, acc[q].w);
+      }
+    }
+    if (pb < cnt) {
+      if ((starts >> pb) & 1u) {
+        flush();
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        head = false;
+        cur = pb;
+      }
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        acc[q].x = fmaf(xb[q].x, db, acc[q].x);
+        acc[q].y = fmaf(xb[q].y, db, acc[q].y);
+        acc[q].z = fmaf(xb[q].z, db, acc[q].z);
+        acc[q].w = fmaf(xb[q].w, db, acc[q].w);
+      }
+    }
+  }
+  // the run that reaches the end of the group
+  if (head) flush();  // the whole group continues an earlier run
+  if (GPW > 1) __syncwarp();
+  if (!head && p0 < cnt) {
+    for (int h = g + 1; h < GPW; ++h) {
+      const int ph = h * LG;
+      if (ph >= cnt || ((starts >> ph) & 1u)) break;
+      const float4* src = &s_head[wi][h][gl];
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const float4 t = src[LG * q];
+        acc[q].x += t.x; acc[q].y += t.y; acc[q].z += t.z; acc[q].w += t.w;
+      }
+      const unsigned later = LG == 32 ? starts : (starts >> ph) & ((1u << (LG & 31)) - 1u);
+      if (later) break;  // the run ended inside group h
+    }
+    flush();
   }
 }
 
 // ---------------------------- K2: dense write ------------------------------
-// smem: rows[<=T][c + 4] | slot[T] (0 = empty voxel, else row + 1)
-//       | carry_lo[T], carry_n[T] (carry rows X[lo+1 .. lo+n] of each interval)
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
+// smem: rows[T + 1][c + 4] (row T stays zero: the row of an empty voxel)
+//       | slot[T] (row of each voxel) | carry_lo[T], carry_n[T] (carry rows
+//       X[lo+1 .. lo+n] of each interval)
 template <int T>
-__device__ __forceinline__ void dense_write_role(
-    int tile, const float* __restrict__ V, const float* __restrict__ X,
+__global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
+    const float* __restrict__ V, const float* __restrict__ X,
     const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
     const int* __restrict__ interval_starts,
-    const int* __restrict__ interval_lengths, const int* __restrict__ meta,
-    const int* __restrict__ flags, int c, int64_t zyx, int tiles_per_b,
+    const int* __restrict__ interval_lengths, int c, int zyx,
     float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int pitch = c + 4;  // 16-byte aligned rows
-  float* rows = reinterpret_cast<float*>(smem_raw);              // [T][pitch]
-  int* slot = reinterpret_cast<int*>(rows + (size_t)T * pitch);  // [T]
+  const int pitch = c + 4;  // 16-byte aligned rows, 4-way bank spread
+  float* rows = reinterpret_cast<float*>(smem_raw);  // [T + 1][pitch]
+  int* slot = reinterpret_cast<int*>(rows + (size_t)(T + 1) * pitch);  // [T]
   int* carry_lo = slot + T;
   int* carry_n = carry_lo + T;
 
+  constexpr int kWrThreads = 2 * T, kWrWarps = kWrThreads / kWarp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = tile / tiles_per_b;
-  const int64_t v0 = (int64_t)(tile - b * tiles_per_b) * T;
-  const int nv = (int)min((int64_t)T, zyx - v0);
-  const int64_t rank0 = (int64_t)b * zyx + v0;
+  const int b = blockIdx.y;
+  const int tile = b * gridDim.x + blockIdx.x;
+  const int v0 = blockIdx.x * T;
+  const int nv = min(T, zyx - v0);
   const int i0 = __ldg(tile_first + tile);
   const int i1 = __ldg(tile_first + tile + 1);
   const int nrows = min(i1 - i0, T);
   const int c4 = c >> 2;
-  float* obase = out + (int64_t)b * c * zyx + v0;
   constexpr int LPR = T / 4;        // lanes per channel row
   constexpr int RPW = kWarp / LPR;  // rows per warp instruction
   const int g = lane % LPR;
-  float* o = obase + 4 * g + (int64_t)(warp * RPW + lane / LPR) * zyx;
+  const int row0 = warp * RPW + lane / LPR;
+  float* o = out + ((int64_t)b * c + row0) * zyx + v0 + 4 * g;
   const int64_t step = (int64_t)kWrWarps * RPW * zyx;
 
   if (nrows <= 0) {  // empty tile: pure zero stream
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (4 * g < nv)
-      for (int row = warp * RPW + lane / LPR; row < c;
-           row += kWrWarps * RPW, o += step)
+      for (int row = row0; row < c; row += kWrWarps * RPW, o += step)
         st_stream(reinterpret_cast<float4*>(o), z);
     return;
   }
-  // wait for the producers that fold this tile's points
-  if (tid == 0) {
-    const int pa = __ldg(interval_starts + i0);
-    const int pb = i1 < meta[0] ? __ldg(interval_starts + i1) : meta[1];
-    constexpr int kPtsPerCta = kPtsPerWarp * (kSumThreads / kWarp);
-    for (int f = pa / kPtsPerCta; f <= (pb - 1) / kPtsPerCta; ++f)
-      while (ld_acquire(flags + f) == 0) __nanosleep(64);
-  }
-  __syncthreads();
-  // rows of this tile's intervals: contiguous in V, copied asynchronously
+  // rows of this tile's intervals: contiguous in V, copied asynchronously,
+  // one warp per row
   {
     const float4* src = reinterpret_cast<const float4*>(V) + (int64_t)i0 * c4;
-    const int total = nrows * c4;
-    for (int q = tid; q < total; q += kWrThreads) {
-      const int r = q / c4, v = q - r * c4;
-      cp_async16(rows + (size_t)r * pitch + 4 * v, src + q);
-    }
+    for (int r = warp; r < nrows; r += kWrWarps)
+      for (int v = lane; v < c4; v += kWarp)
+        cp_async16(rows + (size_t)r * pitch + 4 * v, src + (size_t)r * c4 + v);
   }
-  for (int q = tid; q < T; q += kWrThreads) slot[q] = 0;
+  for (int q = tid; q < T; q += kWrThreads) slot[q] = T;
+  for (int q = tid; q < pitch; q += kWrThreads) rows[(size_t)T * pitch + q] = 0.f;
   __syncthreads();
+  const int64_t rank0 = (int64_t)b * zyx + v0;
   int any_carry = 0;
   for (int r = tid; r < nrows; r += kWrThreads) {
     const int64_t vl = (int64_t)__ldg(seg_rank + i0 + r) - rank0;
-    if (vl >= 0 && vl < nv) slot[vl] = r + 1;
+    if (vl >= 0 && vl < nv) slot[vl] = r;
     const int st = __ldg(interval_starts + i0 + r);
     const int ln = __ldg(interval_lengths + i0 + r);
     const int lo = st / kPtsPerWarp;
@@ -289,89 +339,56 @@ __device__ __forceinline__ void dense_write_role(
   cp_async_commit_wait_all();
   if (__syncthreads_or(any_carry)) {
     // add the carry rows of intervals that span several K1 slices, in slice
-    // order (deterministic); 8 loads in flight per thread
+    // order (deterministic); one warp per row, 8 loads in flight per lane
     const float4* X4 = reinterpret_cast<const float4*>(X);
-    const int total = nrows * c4;
-    for (int q = tid; q < total; q += kWrThreads) {
-      const int r = q / c4, v = q - r * c4;
+    for (int r = warp; r < nrows; r += kWrWarps) {
       const int nx = carry_n[r];
       if (nx == 0) continue;
-      float4* dst = reinterpret_cast<float4*>(rows + (size_t)r * pitch + 4 * v);
-      float4 a = *dst;
-      const float4* src = X4 + (int64_t)(carry_lo[r] + 1) * c4 + v;
-      for (int k = 0; k < nx; k += 8) {
-        float4 t[8];
+      for (int v = lane; v < c4; v += kWarp) {
+        float4* dst = reinterpret_cast<float4*>(rows + (size_t)r * pitch + 4 * v);
+        float4 a = *dst;
+        const float4* src = X4 + (int64_t)(carry_lo[r] + 1) * c4 + v;
+        for (int k = 0; k < nx; k += 8) {
+          float4 t[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          t[j] = (k + j < nx) ? __ldcg(src + (int64_t)(k + j) * c4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j)
+            t[j] = (k + j < nx) ? __ldcg(src + (int64_t)(k + j) * c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (k + j < nx) {
-            a.x += t[j].x; a.y += t[j].y; a.z += t[j].z; a.w += t[j].w;
+          for (int j = 0; j < 8; ++j) {
+            if (k + j < nx) {
+              a.x += t[j].x; a.y += t[j].y; a.z += t[j].z; a.w += t[j].w;
+            }
           }
         }
+        *dst = a;
       }
-      *dst = a;
     }
     __syncthreads();
   }
 
   if (4 * g < nv) {
+    // four consecutive voxels of one channel per lane; an empty voxel reads the
+    // zero row, so the loop is branch-free: 4 LDS + 1 STG.128 per 16 bytes
     const int4 s4 = *reinterpret_cast<const int4*>(slot + 4 * g);
-    const bool gany = (s4.x | s4.y | s4.z | s4.w) != 0;
-    const float* rx = rows + (size_t)(s4.x - 1) * pitch;
-    const float* ry = rows + (size_t)(s4.y - 1) * pitch;
-    const float* rz = rows + (size_t)(s4.z - 1) * pitch;
-    const float* rw = rows + (size_t)(s4.w - 1) * pitch;
-    for (int row = warp * RPW + lane / LPR; row < c;
-         row += kWrWarps * RPW, o += step) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gany) {
-        if (s4.x) v.x = rx[row];
-        if (s4.y) v.y = ry[row];
-        if (s4.z) v.z = rz[row];
-        if (s4.w) v.w = rw[row];
-      }
+    const float* rx = rows + (size_t)s4.x * pitch;
+    const float* ry = rows + (size_t)s4.y * pitch;
+    const float* rz = rows + (size_t)s4.z * pitch;
+    const float* rw = rows + (size_t)s4.w * pitch;
+#pragma unroll 5
+    for (int row = row0; row < c; row += kWrWarps * RPW, o += step) {
+      float4 v;
+      v.x = rx[row];
+      v.y = ry[row];
+      v.z = rz[row];
+      v.w = rw[row];
       st_stream(reinterpret_cast<float4*>(o), v);
     }
   }
 }
 
-// ------------------------- one launch, two roles ---------------------------
-template <int T, int LG, int VPL>
-__global__ void __launch_bounds__(kPoolThreads) pool_split_kernel(
-    const float* __restrict__ depth, const float* __restrict__ feat,
-    const int* __restrict__ ranks_depth, const int* __restrict__ ranks_feat,
-    const int* __restrict__ ranks_bev, const int* __restrict__ interval_starts,
-    const int* __restrict__ interval_lengths,
-    const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
-    const int* __restrict__ warp_first, const int* __restrict__ meta,
-    int* __restrict__ flags, int n_sum_ctas, int c, int64_t zyx,
-    int tiles_per_b, float* __restrict__ V, float* __restrict__ X,
-    float* __restrict__ out) {
-  if ((int)blockIdx.x < n_sum_ctas) {
-    interval_sums_role<LG, VPL>(blockIdx.x, depth, feat, ranks_depth,
-                                ranks_feat, ranks_bev, interval_starts,
-                                warp_first, meta, c, V, X);
-    // publish: every thread's row stores, then the flag
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + blockIdx.x),
-                   "r"(1)
-                   : "memory");
-    }
-    return;
-  }
-  dense_write_role<T>(blockIdx.x - n_sum_ctas, V, X, tile_first, seg_rank,
-                      interval_starts, interval_lengths, meta, flags, c, zyx,
-                      tiles_per_b, out);
-}
-
-// ------------------------------ host side ---------------------------------
 static inline size_t write_smem_bytes(int T, int c) {
-  return (size_t)T * (c + 4) * 4 + (size_t)3 * T * 4;
+  return (size_t)(T + 1) * (c + 4) * 4 + (size_t)3 * T * 4;
 }
 
 // FBBEV_POOL_TILE overrides the tile size (32 / 64 / 128 voxels) for tuning.
@@ -387,7 +404,8 @@ static int split_pick_tile(int c) {
 }
 
 bool split_supported(int c, int64_t zyx) {
-  return c % 4 == 0 && zyx % 4 == 0 && c >= 4 && c <= 1024 &&
+  return c % 4 == 0 && zyx % 4 == 0 && zyx < (1ll << 31) && c >= 4 &&
+         c <= 1024 &&
          write_smem_bytes(32, c) <= 200 * 1024;
 }
 
@@ -398,7 +416,6 @@ struct SplitWs {
   int* seg_rank;
   int* warp_first;
   int* meta;
-  int* flags;  // [n_sum_ctas] producer-done flags (cleared per launch)
   float* V;    // [n_intervals_max][c]  interval sums
   float* X;    // [n_warps_max][c]      carry rows of producer slices
   int n_warps_max, n_sum_ctas;
@@ -421,8 +438,6 @@ static SplitWs split_layout(void* ws, int batch, int64_t zyx,
   off += up256((size_t)(w.n_warps_max + 1) * 4);
   w.meta = reinterpret_cast<int*>(p + off);
   off += 256;
-  w.flags = reinterpret_cast<int*>(p + off);
-  off += up256((size_t)w.n_sum_ctas * 4);
   w.V = reinterpret_cast<float*>(p + off);
   off += up256((size_t)std::max(n_intervals_max, 1) * c * 4);
   w.X = reinterpret_cast<float*>(p + off);
@@ -460,51 +475,22 @@ int split_plan(const int* ranks_bev, const int* interval_starts,
   return launch_status();
 }
 
-template <int T, int LG, int VPL>
-static int launch_pool(const SplitWs& w, const float* depth, const float* feat,
-                       const int* ranks_depth, const int* ranks_feat,
-                       const int* ranks_bev, const int* interval_starts,
-                       const int* interval_lengths, int n_sum_ctas, int c,
-                       int64_t zyx, int tiles_per_b, int64_t n_tiles,
-                       float* out, cudaStream_t st) {
+template <int T>
+static int launch_write(const SplitWs& w, const int* interval_starts,
+                        const int* interval_lengths, int c, int64_t zyx,
+                        int tiles_per_b, int batch, float* out,
+                        cudaStream_t st) {
   const size_t smem = write_smem_bytes(T, c);
-  auto k = pool_split_kernel<T, LG, VPL>;
+  auto k = dense_write_kernel<T>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(
         k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  k<<<(unsigned)(n_sum_ctas + n_tiles), kPoolThreads, smem, st>>>(
-      depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
-      interval_lengths, w.tile_first, w.seg_rank, w.warp_first, w.meta,
-      w.flags, n_sum_ctas, c, zyx, tiles_per_b, w.V, w.X, out);
+  k<<<dim3((unsigned)tiles_per_b, (unsigned)batch), 2 * T, smem, st>>>(
+      w.V, w.X, w.tile_first, w.seg_rank, interval_starts, interval_lengths, c,
+      (int)zyx, out);
   return launch_status();
-}
-
-template <int T>
-static int launch_pool_t(const SplitWs& w, const float* depth,
-                         const float* feat, const int* ranks_depth,
-                         const int* ranks_feat, const int* ranks_bev,
-                         const int* interval_starts,
-                         const int* interval_lengths, int n_sum_ctas, int c,
-                         int64_t zyx, int tiles_per_b, int64_t n_tiles,
-                         float* out, cudaStream_t st) {
-  const int c4 = c / 4;
-#define FBBEV_POOL_CASE(LGV, VPLV)                                            \
-  return launch_pool<T, LGV, VPLV>(w, depth, feat, ranks_depth, ranks_feat,   \
-                                   ranks_bev, interval_starts,                \
-                                   interval_lengths, n_sum_ctas, c, zyx,      \
-                                   tiles_per_b, n_tiles, out, st)
-  // group width LG and float4 columns per lane VPL with LG * VPL >= C / 4
-  if (c4 <= 4) FBBEV_POOL_CASE(4, 1);
-  if (c4 <= 8) FBBEV_POOL_CASE(4, 2);
-  if (c4 <= 16) FBBEV_POOL_CASE(4, 4);
-  if (c4 <= 20) FBBEV_POOL_CASE(4, 5);
-  if (c4 <= 32) FBBEV_POOL_CASE(4, 8);
-  if (c4 <= 64) FBBEV_POOL_CASE(8, 8);
-  if (c4 <= 128) FBBEV_POOL_CASE(16, 8);
-  FBBEV_POOL_CASE(32, 8);
-#undef FBBEV_POOL_CASE
 }
 
 int split_launch(const float* depth, const float* feat, const int* ranks_depth,
@@ -518,30 +504,38 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
   const int T = split_pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
   const int64_t n_tiles = (int64_t)batch * tiles_per_b;
-  // no producers at all when the index is empty (the plan left meta = 0 and
-  // tile_first = 0, so every tile is an empty tile)
-  const int n_sum_ctas = n_intervals_max > 0 ? w.n_sum_ctas : 0;
-  if (n_sum_ctas > 0) {
-    cudaError_t e = cudaMemsetAsync(w.flags, 0, (size_t)n_sum_ctas * 4, st);
-    if (e != cudaSuccess) return (int)e;
+  if (n_intervals_max > 0) {
+    count_launch();
+    const unsigned grid = (unsigned)w.n_sum_ctas;
+    const int c4 = c / 4;
+#define FBBEV_SUM_CASE(LGV, VPLV)                                             \
+  interval_sums_kernel<LGV, VPLV><<<grid, kSumThreads, 0, st>>>(              \
+      depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,       \
+      w.warp_first, w.meta, c, w.V, w.X)
+    // group width LG and float4 columns per lane VPL with LG * VPL >= C / 4
+    if (c4 <= 4) FBBEV_SUM_CASE(4, 1);
+    else if (c4 <= 8) FBBEV_SUM_CASE(4, 2);
+    else if (c4 <= 16) FBBEV_SUM_CASE(4, 4);
+    else if (c4 <= 20) FBBEV_SUM_CASE(4, 5);
+    else if (c4 <= 32) FBBEV_SUM_CASE(4, 8);
+    else if (c4 <= 64) FBBEV_SUM_CASE(8, 8);
+    else if (c4 <= 128) FBBEV_SUM_CASE(16, 8);
+    else FBBEV_SUM_CASE(32, 8);
+#undef FBBEV_SUM_CASE
+    int rc = launch_status();
+    if (rc) return rc;
   }
   count_launch();
   switch (T) {
     case 128:
-      return launch_pool_t<128>(w, depth, feat, ranks_depth, ranks_feat,
-                                ranks_bev, interval_starts, interval_lengths,
-                                n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
-                                st);
+      return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
+                               tiles_per_b, batch, out, st);
     case 64:
-      return launch_pool_t<64>(w, depth, feat, ranks_depth, ranks_feat,
-                               ranks_bev, interval_starts, interval_lengths,
-                               n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
-                               st);
+      return launch_write<64>(w, interval_starts, interval_lengths, c, zyx,
+                              tiles_per_b, batch, out, st);
     default:
-      return launch_pool_t<32>(w, depth, feat, ranks_depth, ranks_feat,
-                               ranks_bev, interval_starts, interval_lengths,
-                               n_sum_ctas, c, zyx, tiles_per_b, n_tiles, out,
-                               st);
+      return launch_write<32>(w, interval_starts, interval_lengths, c, zyx,
+                              tiles_per_b, batch, out, st);
   }
 }
 
