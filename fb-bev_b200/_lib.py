@@ -53,6 +53,11 @@ _SIGNATURES = {
     "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
     "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p, _p]),
     "fbbev_da_sca_fwd": (ctypes.c_int, [_p] * 10 + [_i32] * 10 + [_p, _p]),
+    "fbbev_linear_packed_bytes": (ctypes.c_size_t, [_i32, _i32]),
+    "fbbev_linear_pack": (ctypes.c_int, [_p, _i32, _i32, _p, _p]),
+    "fbbev_linear_fwd": (ctypes.c_int, [
+        _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i32,
+        ctypes.c_float, _p, _i64, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -1,0 +1,85 @@
+"""Row-wise Linear (+ bias, ReLU, residual, LayerNorm) on the tcgen05 tensor cores.
+
+Host side of ``fbbev_linear_fwd`` (include/fbbev_b200.h): the nn.Linear /
+LayerNorm / residual chain of the reference's encoder layer
+(bevformer_encoder.py:251-377, spatial_cross_attention_depth.py:219, 420-427)
+as one kernel per Linear.  Inference only (no autograd); the modules in
+``view_transformation/backward_projection.py`` use it when gradients are off.
+"""
+import torch
+
+from .. import _lib
+
+MAX_N = 160  # widest column block of one launch
+
+
+class _Packed:
+    __slots__ = ("blocks", "key")
+
+
+_CACHE = {}
+
+
+def _pack(weight):
+    """hi / lo split image of `weight` (n, k), one block per <= 160 columns."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    hit = _CACHE.get(id(weight))
+    if hit is not None and hit.key == key:
+        return hit.blocks
+    L = _lib.lib()
+    n, k = weight.shape
+    w = weight.detach().contiguous().float()
+    blocks = []
+    for n0 in range(0, n, MAX_N):
+        n1 = min(n, n0 + MAX_N)
+        nbytes = L.fbbev_linear_packed_bytes(n1 - n0, k)
+        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=w.device)
+        _lib.check(L.fbbev_linear_pack(_lib.ptr(w[n0:n1]), n1 - n0, k, _lib.ptr(buf),
+                                       _lib.stream_ptr(w.device)), "fbbev_linear_pack")
+        blocks.append((n0, n1, buf))
+    ent = _Packed()
+    ent.blocks, ent.key = blocks, key
+    _CACHE[id(weight)] = ent
+    return blocks
+
+
+def supported(x, weight):
+    n, k = weight.shape
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and k % 4 == 0 and n % 4 == 0 and not torch.is_grad_enabled())
+
+
+def linear_fused(x, weight, bias=None, relu=False, residual=None, ln_weight=None,
+                 ln_bias=None, eps=1e-5):
+    """``LN(act(x @ weight.T + bias) + residual)`` with every part optional."""
+    _lib.require_cuda(x)
+    n, k = weight.shape
+    assert x.shape[-1] == k
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(-1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    m = x2.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, n)
+        if r2.stride(-1) != 1 or r2.stride(0) % 4 or r2.data_ptr() % 16:
+            r2 = r2.contiguous()
+    blocks = _pack(weight)
+    if len(blocks) > 1 and ln_weight is not None:
+        raise _lib.FbbevError("LayerNorm epilogue needs n <= %d" % MAX_N)
+    L = _lib.lib()
+    sp = _lib.stream_ptr(x.device)
+    b = bias.detach().contiguous() if bias is not None else None
+    for n0, n1, buf in blocks:
+        _lib.check(L.fbbev_linear_fwd(
+            _lib.ptr(x2), x2.stride(0), _lib.ptr(buf),
+            _lib.ptr(b[n0:n1]) if b is not None else None,
+            _lib.ptr(r2[:, n0:n1]) if r2 is not None else None,
+            r2.stride(0) if r2 is not None else 0,
+            _lib.ptr(ln_weight) if ln_weight is not None else None,
+            _lib.ptr(ln_bias) if ln_bias is not None else None,
+            m, k, n1 - n0, int(bool(relu)), float(eps),
+            _lib.ptr(y[:, n0:n1]), y.stride(0), sp), "fbbev_linear_fwd")
+    return y.view(*lead, n)

@@ -299,6 +299,38 @@ int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
                      int32_t heads, int32_t ch, int32_t levels, int32_t points,
                      int32_t Z, int32_t DC, float* out, fbbev_stream_t stream);
 
+/* ---- row-wise Linear (+ bias, ReLU, residual, LayerNorm) on tcgen05 ---------
+ * Replaces the nn.Linear / LayerNorm / residual chain of the reference's
+ * encoder layer for the backward projection: sampling_offsets,
+ * attention_weights, value_proj, output_proj
+ * (spatial_cross_attention_depth.py:420-427, 226-233; mmcv
+ * MultiScaleDeformableAttention), mmcv FFN and the `norm` entries of
+ * operation_order (bevformer_encoder.py:251-377), which the reference runs as
+ * cuBLAS fp32 GEMMs plus separate elementwise kernels.
+ *
+ *   y = LN( act( x . W^T + bias ) + residual )
+ *
+ * x (m, k) fp32 with row stride ldx floats, W (n, k) as in nn.Linear.weight,
+ * y (m, n) with row stride ldy (a column block of a wider output is allowed);
+ * bias / residual (m, n; row stride ldr) / ln_weight+ln_bias (n) are optional
+ * (NULL), relu != 0
+ * applies ReLU before the residual.  fp32 in and out; products are formed as
+ * 3xTF32 on the tensor cores (error ~1e-6 relative, inside the 1e-4 bar; plain
+ * TF32 is not).  Weights are packed once (hi / lo split in the shared-memory
+ * layout of the kernel) with fbbev_linear_pack into fbbev_linear_packed_bytes
+ * bytes; k % 4 == 0, n % 4 == 0, n <= 160 (split wider layers over n),
+ * 16-byte aligned pointers; otherwise FBBEV_ERR_UNSUPPORTED /
+ * FBBEV_ERR_INVALID_ARGUMENT.
+ */
+size_t fbbev_linear_packed_bytes(int32_t n, int32_t k);
+int fbbev_linear_pack(const float* weight, int32_t n, int32_t k, float* packed,
+                      fbbev_stream_t stream);
+int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
+                     const float* bias, const float* residual, int64_t ldr,
+                     const float* ln_weight, const float* ln_bias, int64_t m,
+                     int32_t k, int32_t n, int32_t relu, float ln_eps, float* y,
+                     int64_t ldy, fbbev_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
