@@ -16,15 +16,20 @@
 //     x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo        (error ~2^-21 relative)
 // three tcgen05.mma.kind::tf32 per k-step into the same fp32 TMEM accumulator.
 //
-// Structure (one persistent CTA per SM, 128-row tiles, 9 warps):
-//   warps 4-7  loaders: X rows -> registers -> hi / lo split -> shared memory in
-//              the UMMA canonical K-major layout (8x16-byte core matrices, no
-//              swizzle); one lane also starts the 1-D bulk copy (TMA) of the
-//              pre-packed weight block of the stage;
-//   warp  8    one lane issues the MMAs (M=128, N<=160, K=8 per instruction),
-//              tcgen05.commit releases the stage / publishes the accumulator;
-//   warps 0-3  epilogue: tcgen05.ld (lane == row), bias / ReLU / residual /
-//              LayerNorm in registers, row stores.
+// Structure (one persistent CTA per SM owning a contiguous range of rows, cut
+// into 128-row tiles; 14 warps):
+//   warps 4-7   loaders: X rows -> registers (two K-blocks in flight per
+//               thread) -> hi / lo split -> shared memory in the UMMA canonical
+//               K-major layout (8x16-byte core matrices, no swizzle);
+//   warp  13    one lane starts the 1-D bulk copy (TMA) of the pre-packed weight
+//               block of a stage as soon as the stage is free;
+//   warp  12    one lane issues the MMAs (M=128, N<=160, K=8 per instruction),
+//               tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 0-3, 8-11  two epilogue groups, one per TMEM accumulator (even / odd
+//               tiles): tcgen05.ld (lane == row), bias / ReLU / residual /
+//               LayerNorm in registers, row stores.  The epilogue is the
+//               longest stage per tile (ncu: one warp per scheduler, dependent
+//               issue), hence two groups.
 //   Ring of K-blocks of 40 floats (5 k-steps) between loaders and MMA, two
 //   accumulators in TMEM between MMA and epilogue.
 #include "common.cuh"
@@ -36,10 +41,16 @@ constexpr int kChunks = kKB / 4;                 // 16-byte chunks per row
 constexpr int kTileM = 128;
 constexpr int kAPart = kTileM * kKB * 4;         // bytes of A_hi (== A_lo)
 constexpr int kAChunkStride = (kTileM / 8) * 128;  // bytes between K chunks
-constexpr int kLinThreads = 288;
+constexpr int kLinThreads = 448;  // 14 warps, see the role table above
 constexpr int kMaxN = 160;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 232448 - 1024;
+constexpr int kSlabPitch = 20;  // floats: 16 columns + 4 (bank spread)
+constexpr int kSlabBytes = 2 * kTileM * kSlabPitch * 4;  // both groups
+// control area after the stages: mbarriers + TMEM slot (256 B), then bias /
+// LayerNorm weight / LayerNorm bias staged once (the L1 left beside ~220 KB of
+// shared memory is too small to keep them: a __ldg would be an L2 round trip)
+constexpr int kCtrlBytes = 256 + 3 * kMaxN * 4;
 
 // ------------------------------- PTX wrappers --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -131,6 +142,24 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+#ifdef LIN_TRACE
+// timeline of CTA 0: every tracing thread appends (tag, clock) to its own
+// shared-memory lane; dumped to global memory at the end of the kernel
+__device__ long long g_trace[512];
+__device__ int g_trace_n;
+#define TRACE_DECL __shared__ long long s_trace[8][64]; __shared__ int s_trace_n[8];
+#define TRACE(lane_, tag)                                                    \
+  do {                                                                       \
+    if (blockIdx.x == 0) {                                                   \
+      const int ti_ = s_trace_n[lane_]++;                                    \
+      if (ti_ < 32) { s_trace[lane_][2 * ti_] = (tag); s_trace[lane_][2 * ti_ + 1] = clock64(); } \
+    }                                                                        \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(lane_, tag) do {} while (0)
+#endif
+
 // ------------------------------ weight packing -------------------------------
 // W [N][K] row-major -> [k-block][hi, lo][chunk 0..9][Npad / 8][8 rows][4]:
 // exactly the shared-memory image of one stage, so a stage's weights are one
@@ -169,15 +198,20 @@ struct LinearParams {
   const float* gamma;     // LayerNorm weight [N] or null
   const float* beta;      // LayerNorm bias [N] or null
   float* y;               // [M][N]
-  int M, K, N, npad, n_kb, relu, n_tiles, stages;
+  int M, K, N, npad, n_kb, relu, rows_per_cta, stages;
+  int slab_pitch;  // floats per slab row: 20 (16-column chunks) or N + 4 (whole rows)
   int64_t ldx, ldr, ldy;  // row strides in floats
   float eps;
 };
 
-template <int NC16, bool LN>
+template <bool LN>
 __global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32_kernel(const LinearParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  TRACE_DECL
+#ifdef LIN_TRACE
+  if (threadIdx.x < 8) s_trace_n[threadIdx.x] = 0;
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npad = p.npad, S = p.stages;
   const uint32_t w_part = (uint32_t)npad * kKB * 4;        // bytes of W_hi
@@ -191,7 +225,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 16 * S + 32);
   const uint32_t smem_base = smem_u32(smem);
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_full + 8u * s, 128 + 1);  // loader threads + expect_tx
@@ -212,52 +246,71 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::
                      : "memory");
   }
+  float* s_bias = reinterpret_cast<float*>(ctrl + 256);
+  float* s_gamma = s_bias + kMaxN;
+  float* s_beta = s_gamma + kMaxN;
+  for (int j = threadIdx.x; j < kMaxN; j += kLinThreads) {
+    s_bias[j] = (p.bias && j < p.N) ? p.bias[j] : 0.f;
+    s_gamma[j] = (p.gamma && j < p.N) ? p.gamma[j] : 1.f;
+    s_beta[j] = (p.beta && j < p.N) ? p.beta[j] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE(0, 1);
+  // this CTA's rows and 128-row tiles (the last one may be partial)
+  const int row_begin = blockIdx.x * p.rows_per_cta;
+  const int row_end = min(p.M, row_begin + p.rows_per_cta);
+  const int n_my = row_end > row_begin ? (row_end - row_begin + kTileM - 1) / kTileM : 0;
 
   if (warp >= 4 && warp < 8) {
     // ================================ loaders ================================
     const int lw = warp - 4;
-    const int lt = threadIdx.x - 128;
     const int r_lo = lane & 15, c_lo = lane >> 4;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int row0 = tile * kTileM;
-      for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+    const int total = n_my * p.n_kb;  // (tile, K-block) items, two per round
+    for (int w0 = 0; w0 < total; w0 += 2) {
+      float4 v[2][10];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int w = w0 + u;
+        const int ti = w / p.n_kb, kb = w - ti * p.n_kb;
+        // rows (2 lw + h) * 16 + r_lo, h = 0 / 1; columns kb*40 + 8 cp + 4 c_lo
+        const int g0 = row_begin + ti * kTileM + lw * 32 + r_lo;
+        const int col0 = kb * kKB + 4 * c_lo;
+        const float* b0 = p.x + (size_t)g0 * p.ldx + col0;
+        const float* b1 = b0 + (size_t)16 * p.ldx;
+        const bool ok0 = w < total && g0 < row_end;
+        const bool ok1 = w < total && g0 + 16 < row_end;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int cp = i % 5;
+          const bool ok = (i < 5 ? ok0 : ok1) && col0 + 8 * cp < p.K;
+          v[u][i] = ok ? __ldg(reinterpret_cast<const float4*>(
+                             (i < 5 ? b0 : b1) + 8 * cp))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (threadIdx.x == 128) TRACE(1, 100 + w0);
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t it = (uint32_t)(w0 + u);
+        if ((int)it >= total) break;
         const uint32_t s = it % S, ph = (it / S) & 1u;
         mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-        const uint32_t st = smem_base + s * stage_bytes;
-        if (lt == 0) {
-          mbar_arrive_expect_tx(bar_full + 8u * s, 2u * w_part);
-          bulk_g2s(st + 2u * kAPart, p.wp + (size_t)kb * (2u * w_part / 4u),
-                   2u * w_part, bar_full + 8u * s);
-        }
-        float4 v[10];
+        if (threadIdx.x == 128) TRACE(1, 200 + it);
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
           const int idx = lw * 10 + i;
           const int row = (idx / 5) * 16 + r_lo;
           const int ch = (idx % 5) * 2 + c_lo;
-          const int grow = min(row0 + row, p.M - 1);
-          const int col = kb * kKB + ch * 4;
-          v[i] = col < p.K ? __ldg(reinterpret_cast<const float4*>(
-                                 p.x + (size_t)grow * p.ldx + col))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int idx = lw * 10 + i;
-          const int row = (idx / 5) * 16 + r_lo;
-          const int ch = (idx % 5) * 2 + c_lo;
+          const float4 x = v[u][i];
           float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-          hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-          hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-          hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-          lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y;
-          lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
+          hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          lo.x = x.x - hi.x; lo.y = x.y - hi.y;
+          lo.z = x.z - hi.z; lo.w = x.w - hi.w;
           const uint32_t off =
               (uint32_t)(ch * (kTileM / 8) + (row >> 3)) * 128u + (row & 7) * 16u;
           unsigned char* a = smem + (size_t)s * stage_bytes + off;
@@ -266,9 +319,24 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8u * s);
+        if (threadIdx.x == 128) TRACE(1, 300 + it);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 13) {
+    // ============================ weight producer ============================
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)(n_my * p.n_kb);
+      for (uint32_t it = 0; it < total; ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1u;
+        mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8u * s, 2u * w_part);
+        bulk_g2s(smem_base + s * stage_bytes + 2u * kAPart,
+                 p.wp + (size_t)(it % p.n_kb) * (2u * w_part / 4u), 2u * w_part,
+                 bar_full + 8u * s);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 12) {
     // ================================ MMA issue ===============================
     if (lane == 0) {
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = npad
@@ -276,7 +344,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                              ((uint32_t)(npad >> 3) << 17) | (8u << 24);
       const uint32_t lbo_b = (uint32_t)npad * 16u;
       uint32_t it = 0, tc = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tc) {
+      for (int ti = 0; ti < n_my; ++ti, ++tc) {
         const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
         mbar_wait(bar_tempty + 8u * acc, aph ^ 1u);
         tc_fence_after();
@@ -285,6 +353,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           const uint32_t s = it % S, ph = (it / S) & 1u;
           mbar_wait(bar_full + 8u * s, ph);
           tc_fence_after();
+          TRACE(2, 400 + it);
           const uint32_t a_hi = smem_base + s * stage_bytes;
           const uint32_t a_lo = a_hi + kAPart;
           const uint32_t w_hi = a_lo + kAPart;
@@ -303,80 +372,228 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           tc_commit(bar_empty + 8u * s);
         }
         tc_commit(bar_tfull + 8u * acc);
+        TRACE(2, 500 + tc);
       }
     }
     __syncwarp();
   } else {
     // ================================ epilogue ================================
+    // group 0 (warps 0-3) drains accumulator 0 = even tiles of this CTA, group 1
+    // (warps 8-11) accumulator 1 = odd tiles; warp % 4 selects the TMEM lanes.
+    // tcgen05.ld hands every thread one row, which is the wrong shape for
+    // global memory (32 rows per request), so residual and output go through a
+    // shared-memory slab per group: whole rows (pitch N + 4) for the LayerNorm
+    // epilogue -- the row lives there between the passes, the residual is
+    // prefetched into it with cp.async before the accumulator is ready, and the
+    // result leaves it fully coalesced -- or 16 columns at a time (pitch 20)
+    // otherwise.  Loops are kept rolled on purpose: straight-line code this
+    // long ran at ~10 cycles per instruction on instruction fetch alone.
     const int N = p.N;
+    const int nc16 = npad >> 4;
+    const uint32_t grp = warp >> 3;
+    const int q = warp & 3;
+    const int gt = q * 32 + lane;  // thread within the group == row of the tile
+    const int pitch = p.slab_pitch;
+    float* slab = reinterpret_cast<float*>(ctrl + kCtrlBytes) +
+                  (size_t)grp * kTileM * pitch;
+    float* my_row = slab + (size_t)gt * pitch;
+    const float4* bias4 = reinterpret_cast<const float4*>(s_bias);
+    const int crow = gt >> 2, cq = gt & 3;  // cooperative mapping: 4 lanes per row
+    const int bar_id = 1 + (int)grp;
+    auto group_sync = [&]() {
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    };
     uint32_t tc = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tc) {
-      const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-      mbar_wait(bar_tfull + 8u * acc, aph);
-      tc_fence_after();
+    for (int ti = 0; ti < n_my; ++ti, ++tc) {
+      if ((tc & 1u) != grp) continue;
+      const uint32_t aph = (tc >> 1) & 1u;
+      const int row0 = row_begin + ti * kTileM;
       const uint32_t taddr =
-          tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)npad;
-      float v[NC16 * 16];
-#pragma unroll
-      for (int c = 0; c < NC16; ++c) tmem_ld16(taddr + 16u * c, v + 16 * c);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8u * acc);
-
-      const int grow = tile * kTileM + warp * 32 + lane;
-      if (grow < p.M) {
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < NC16 * 16; ++j)
-            if (j < N) v[j] += __ldg(p.bias + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < NC16 * 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
+          tmem_base + ((uint32_t)(q * 32) << 16) + grp * (uint32_t)npad;
+      if (LN) {
+        group_sync();  // the previous tile's rows have left the slab
         if (p.residual) {
-          const float4* r =
-              reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr);
+#pragma unroll 1
+          for (int c = 0; c < nc16; ++c) {
+            const int col = 16 * c + 4 * cq;
 #pragma unroll
-          for (int j = 0; j < NC16 * 4; ++j)
-            if (4 * j < N) {
-              const float4 t = __ldg(r + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y;
-              v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            for (int i = 0; i < 4; ++i) {
+              const int r = crow + 32 * i;
+              const bool ok = row0 + r < row_end && col < N;
+              const float* src = p.residual +
+                                 (size_t)(ok ? row0 + r : row_begin) * p.ldr +
+                                 (ok ? col : 0);
+              const uint32_t dst = smem_u32(slab + (size_t)r * pitch + col);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                           "l"(src), "r"(ok ? 16 : 0)
+                           : "memory");
             }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        if (LN) {
-          float mean = 0.f;
+        if (gt == 0) TRACE(3 + grp, 600 + tc);
+        mbar_wait(bar_tfull + 8u * grp, aph);
+        tc_fence_after();
+        if (gt == 0) TRACE(3 + grp, 700 + tc);
+        if (p.residual) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          group_sync();
+        }
+        // pass 1: accumulator + bias (+ ReLU) + residual -> my slab row, sum
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nc16; ++c) {
+          float v[16];
+          tmem_ld16(taddr + 16u * c, v);
+          tmem_ld_wait();
+          if (c == nc16 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8u * grp);
+          }
 #pragma unroll
-          for (int j = 0; j < NC16 * 16; ++j)
-            if (j < N) mean += v[j];
-          mean /= (float)N;
-          float var = 0.f;
-#pragma unroll
-          for (int j = 0; j < NC16 * 16; ++j)
-            if (j < N) {
-              const float dlt = v[j] - mean;
-              var = fmaf(dlt, dlt, var);
+          for (int j = 0; j < 4; ++j) {
+            const int col = 16 * c + 4 * j;
+            if (col < N) {
+              const float4 bb = bias4[col >> 2];
+              float4 t = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y,
+                                     v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+              if (p.relu) {
+                t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f);
+                t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+              }
+              float4* cell = reinterpret_cast<float4*>(my_row + col);
+              if (p.residual) {
+                const float4 r = *cell;
+                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+              }
+              *cell = t;
+              sum += (t.x + t.y) + (t.z + t.w);
             }
-          const float rstd = rsqrtf(var / (float)N + p.eps);
-#pragma unroll
-          for (int j = 0; j < NC16 * 16; ++j)
-            if (j < N)
-              v[j] = fmaf((v[j] - mean) * rstd, __ldg(p.gamma + j),
-                          __ldg(p.beta + j));
+          }
         }
-        float4* o = reinterpret_cast<float4*>(p.y + (size_t)grow * p.ldy);
+        if (gt == 0) TRACE(3 + grp, 800 + tc);
+        // pass 2 / 3: variance about the mean, normalise in place
+        const int c4 = N >> 2;
+        const float mean = sum / (float)N;
+        float var = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < c4; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(my_row + 4 * j);
+          const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+          var += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(var / (float)N + p.eps);
+        const float4* g4 = reinterpret_cast<const float4*>(s_gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(s_beta);
+#pragma unroll 4
+        for (int j = 0; j < c4; ++j) {
+          float4* cell = reinterpret_cast<float4*>(my_row + 4 * j);
+          const float4 t = *cell, g = g4[j], b = b4[j];
+          *cell = make_float4(fmaf((t.x - mean) * rstd, g.x, b.x),
+                              fmaf((t.y - mean) * rstd, g.y, b.y),
+                              fmaf((t.z - mean) * rstd, g.z, b.z),
+                              fmaf((t.w - mean) * rstd, g.w, b.w));
+        }
+        if (gt == 0) TRACE(3 + grp, 900 + tc);
+        group_sync();
+        // whole rows slab -> global: consecutive lanes, consecutive 16 bytes
+        {
+          int r = gt / c4, ch = gt - r * c4;
+          const int dq = 128 / c4, dr = 128 - dq * c4;
+#pragma unroll 1
+          while (r < kTileM) {
+            float4 t[4];
+            int rr[4], cc[4];
 #pragma unroll
-        for (int j = 0; j < NC16 * 4; ++j)
-          if (4 * j < N)
-            o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int u = 0; u < 4; ++u) {
+              rr[u] = r; cc[u] = ch;
+              if (r < kTileM)
+                t[u] = *reinterpret_cast<const float4*>(slab + (size_t)r * pitch + 4 * ch);
+              r += dq; ch += dr;
+              if (ch >= c4) { ch -= c4; ++r; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (rr[u] < kTileM && row0 + rr[u] < row_end)
+                *reinterpret_cast<float4*>(
+                    p.y + (size_t)(row0 + rr[u]) * p.ldy + 4 * cc[u]) = t[u];
+          }
+        }
+        if (gt == 0) TRACE(3 + grp, 1000 + tc);
+      } else {
+        mbar_wait(bar_tfull + 8u * grp, aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < nc16; ++c) {
+          float v[16];
+          tmem_ld16(taddr + 16u * c, v);
+          tmem_ld_wait();
+          if (c == nc16 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8u * grp);
+          }
+          const int col = 16 * c + 4 * cq;
+          if (p.residual) {  // 16 columns: global -> slab (64 B per row) -> row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = crow + 32 * i;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row0 + r < row_end && col < N)
+                t = __ldg(reinterpret_cast<const float4*>(
+                    p.residual + (size_t)(row0 + r) * p.ldr + col));
+              *reinterpret_cast<float4*>(slab + (size_t)r * pitch + 4 * cq) = t;
+            }
+            group_sync();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (16 * c + 4 * j < N) {
+              const float4 bb = bias4[4 * c + j];
+              t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+            }
+            if (p.relu) {
+              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f);
+              t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            float4* cell = reinterpret_cast<float4*>(my_row + 4 * j);
+            if (p.residual) {
+              const float4 r = *cell;
+              t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+            }
+            *cell = t;
+          }
+          group_sync();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = crow + 32 * i;
+            if (row0 + r < row_end && col < N)
+              *reinterpret_cast<float4*>(p.y + (size_t)(row0 + r) * p.ldy + col) =
+                  *reinterpret_cast<const float4*>(slab + (size_t)r * pitch + 4 * cq);
+          }
+          group_sync();
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (threadIdx.x == 0) TRACE(0, 2);
+#ifdef LIN_TRACE
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int n = 0;
+    for (int l = 0; l < 8; ++l)
+      for (int i = 0; i < min(s_trace_n[l], 32); ++i) {
+        g_trace[2 * n] = s_trace[l][2 * i];
+        g_trace[2 * n + 1] = s_trace[l][2 * i + 1];
+        ++n;
+      }
+    g_trace_n = n;
+  }
+#endif
+  if (warp == 12) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(
                      tmem_base),
@@ -388,13 +605,16 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 static inline int pad16(int n) { return (n + 15) / 16 * 16; }
 static inline int n_kblocks(int k) { return (k + kKB - 1) / kKB; }
 
-template <int NC16>
 static int launch_linear(const LinearParams& p, bool ln, size_t smem, int grid,
                          cudaStream_t st) {
-  auto kern = ln ? linear_tf32_kernel<NC16, true> : linear_tf32_kernel<NC16, false>;
-  cudaError_t e = cudaFuncSetAttribute(
-      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  auto kern = ln ? linear_tf32_kernel<true> : linear_tf32_kernel<false>;
+  static size_t allowed[2] = {0, 0};
+  if (smem > allowed[ln]) {
+    cudaError_t e = cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    allowed[ln] = smem;
+  }
   kern<<<grid, kLinThreads, smem, st>>>(p);
   return launch_status();
 }
@@ -402,6 +622,16 @@ static int launch_linear(const LinearParams& p, bool ln, size_t smem, int grid,
 }  // namespace fbbev
 
 using namespace fbbev;
+
+#ifdef LIN_TRACE
+FBBEV_API int fbbev_debug_linear_trace(long long* out, int reset) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 512);
+  if (reset) { int z = 0; cudaMemcpyToSymbol(g_trace_n, &z, sizeof(int)); }
+  return n;
+}
+#endif
 
 FBBEV_API size_t fbbev_linear_packed_bytes(int32_t n, int32_t k) {
   if (n <= 0 || k <= 0) return 0;
@@ -446,13 +676,24 @@ FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
   p.M = (int)m; p.K = k; p.N = n; p.npad = pad16(n); p.n_kb = n_kblocks(k);
   p.relu = relu; p.eps = ln_eps;
   p.ldx = ldx; p.ldr = ldr; p.ldy = ldy;
-  p.n_tiles = (int)ceil_div64(m, kTileM);
   const size_t stage = 2 * (size_t)kAPart + 2 * (size_t)p.npad * kKB * 4;
-  int stages = (int)((kSmemLimit - 256) / stage);
+  // LayerNorm epilogue: whole-row slabs (residual prefetch, fully coalesced
+  // stores) when they fit beside two pipeline stages, else 16-column chunks
+  const bool ln = ln_weight != nullptr;
+  size_t slab_bytes = kSlabBytes;
+  p.slab_pitch = kSlabPitch;
+  const size_t wide_bytes = 2 * (size_t)kTileM * (n + 4) * 4;
+  if (ln) {
+    if (2 * stage + kCtrlBytes + wide_bytes > (size_t)kSmemLimit)
+      return FBBEV_ERR_UNSUPPORTED;  // n <= 80 with the 40-float K-block
+    slab_bytes = wide_bytes;
+    p.slab_pitch = n + 4;
+  }
+  int stages = (int)((kSmemLimit - kCtrlBytes - slab_bytes) / stage);
   stages = stages > 4 ? 4 : stages;
   if (stages < 2) return FBBEV_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem = stages * stage + 256;
+  const size_t smem = stages * stage + kCtrlBytes + slab_bytes;
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
@@ -460,21 +701,12 @@ FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const int grid = p.n_tiles < n_sm ? p.n_tiles : n_sm;
-  const bool ln = ln_weight != nullptr;
+  // equal contiguous row ranges (multiples of 8 rows), one CTA per SM
+  const int n_tiles = (int)ceil_div64(m, kTileM);
+  int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  p.rows_per_cta = (int)(ceil_div64(ceil_div64(m, grid), 8) * 8);
+  grid = (int)ceil_div64(m, p.rows_per_cta);
   cudaStream_t st = as_stream(stream);
   count_launch();
-  switch (p.npad / 16) {
-    case 1: return launch_linear<1>(p, ln, smem, grid, st);
-    case 2: return launch_linear<2>(p, ln, smem, grid, st);
-    case 3: return launch_linear<3>(p, ln, smem, grid, st);
-    case 4: return launch_linear<4>(p, ln, smem, grid, st);
-    case 5: return launch_linear<5>(p, ln, smem, grid, st);
-    case 6: return launch_linear<6>(p, ln, smem, grid, st);
-    case 7: return launch_linear<7>(p, ln, smem, grid, st);
-    case 8: return launch_linear<8>(p, ln, smem, grid, st);
-    case 9: return launch_linear<9>(p, ln, smem, grid, st);
-    case 10: return launch_linear<10>(p, ln, smem, grid, st);
-    default: return FBBEV_ERR_UNSUPPORTED;
-  }
+  return launch_linear(p, ln, smem, grid, st);
 }

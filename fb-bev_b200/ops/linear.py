@@ -43,6 +43,14 @@ def _pack(weight):
     return blocks
 
 
+def ln_supported(n):
+    """The LayerNorm epilogue keeps whole rows in shared memory beside two
+    pipeline stages (linear_tf32.cu): n <= 80 with the 40-float K-block."""
+    npad = (n + 15) // 16 * 16
+    stage = 2 * 128 * 40 * 4 + 2 * npad * 40 * 4
+    return 2 * stage + 256 + 3 * MAX_N * 4 + 2 * 128 * (n + 4) * 4 <= 232448 - 1024
+
+
 def supported(x, weight):
     n, k = weight.shape
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
@@ -67,8 +75,8 @@ def linear_fused(x, weight, bias=None, relu=False, residual=None, ln_weight=None
         if r2.stride(-1) != 1 or r2.stride(0) % 4 or r2.data_ptr() % 16:
             r2 = r2.contiguous()
     blocks = _pack(weight)
-    if len(blocks) > 1 and ln_weight is not None:
-        raise _lib.FbbevError("LayerNorm epilogue needs n <= %d" % MAX_N)
+    if ln_weight is not None and not ln_supported(n):
+        raise _lib.FbbevError("LayerNorm epilogue: n = %d does not fit" % n)
     L = _lib.lib()
     sp = _lib.stream_ptr(x.device)
     b = bias.detach().contiguous() if bias is not None else None

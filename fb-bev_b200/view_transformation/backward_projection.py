@@ -22,10 +22,13 @@ Registry names, constructor keywords, ``forward`` signatures and state-dict
 keys match, so a FB-OCC checkpoint loads and the detector's call
 (``fbocc.py:357-363``) is unchanged.
 
-What runs where: the dense Linears / LayerNorm / FFN stay on cuBLAS through
-PyTorch; everything between them -- softmax, sampling-location arithmetic, the
-depth look-up, bilinear sampling, the per-camera accumulation and averaging --
-is one hand-written kernel per attention (``fbbev_msda_fused_fwd`` for the
+What runs where: with gradients off (inference), every nn.Linear runs on the
+tcgen05 tensor cores through ``fbbev_linear_fwd`` (3xTF32, fp32 in / out) with
+the bias, ReLU, residual add and the following LayerNorm in its epilogue; with
+gradients on they stay on cuBLAS through PyTorch (``FBBEV_TORCH_LINEAR=1`` forces
+that path).  Everything between them -- softmax, sampling-location arithmetic,
+the depth look-up, bilinear sampling, the per-camera accumulation and averaging
+-- is one hand-written kernel per attention (``fbbev_msda_fused_fwd`` for the
 self-attention, ``fbbev_da_sca_fwd`` for the depth-aware cross-attention).  The
 reference's per-camera ``nonzero()`` loops, zero-padded re-batching, int64
 one-hot tensor and scatter loops (spatial_cross_attention_depth.py:156-216) have
@@ -40,6 +43,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops import linear as _linear_ops
 from ..ops import ms_deform_attn as _msda_ops
 from ..ops.ms_deform_attn import (MultiScaleDeformableAttnFunction_fp32,
                                   da_spatial_cross_attention_core,
@@ -70,6 +74,35 @@ def _const_tensor(values, device):
         t = torch.tensor(values, dtype=torch.long, device=device)
         _CONST_CACHE[key] = t
     return t
+
+
+def _fused_linear_on(x, *dropouts):
+    """The tensor-core Linear path: CUDA fp32 input, no autograd, no active
+    dropout."""
+    if os.environ.get('FBBEV_TORCH_LINEAR', '0') == '1':
+        return False
+    if torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32:
+        return False
+    for d in dropouts:
+        if isinstance(d, nn.Dropout) and d.training and d.p > 0:
+            return False
+    return True
+
+
+def _linear(mod, x, relu=False, residual=None, norm=None):
+    """``norm(act(mod(x)) + residual)`` in one kernel launch per <= 160 output
+    columns (``mod`` an nn.Linear, ``norm`` an nn.LayerNorm or None)."""
+    n, k = mod.weight.shape
+    if k % 4 or n % 4 or (norm is not None and not _linear_ops.ln_supported(n)):
+        y = mod(x)
+        y = F.relu(y) if relu else y
+        y = y + residual if residual is not None else y
+        return norm(y) if norm is not None else y
+    return _linear_ops.linear_fused(
+        x, mod.weight, mod.bias, relu=relu, residual=residual,
+        ln_weight=None if norm is None else norm.weight,
+        ln_bias=None if norm is None else norm.bias,
+        eps=1e-5 if norm is None else norm.eps)
 
 
 def _xavier_uniform(module, bias=0.):
@@ -159,13 +192,22 @@ class FFN(BaseModule):
         self.dropout_layer = nn.Dropout(p) if p > 0 else nn.Identity()
         self.add_identity = add_identity
 
-    def forward(self, x, identity=None):
+    def forward(self, x, identity=None, post_norm=None):
+        drops = [m for m in self.layers.modules() if isinstance(m, nn.Dropout)]
+        if (_fused_linear_on(x, self.dropout_layer, *drops) and
+                all(isinstance(l[1], nn.ReLU) for l in self.layers[:-2])):
+            out = x
+            for l in self.layers[:-2]:
+                out = _linear(l[0], out, relu=True)
+            res = (identity if identity is not None else x) \
+                if self.add_identity else None
+            return _linear(self.layers[-2], out, residual=res, norm=post_norm)
         out = self.layers(x)
-        if not self.add_identity:
-            return self.dropout_layer(out)
-        if identity is None:
-            identity = x
-        return identity + self.dropout_layer(out)
+        if self.add_identity:
+            out = (x if identity is None else identity) + self.dropout_layer(out)
+        else:
+            out = self.dropout_layer(out)
+        return out if post_norm is None else post_norm(out)
 
 
 # ---------------------------------------------------------------------------
@@ -215,7 +257,8 @@ class MultiScaleDeformableAttention(BaseModule):
 
     def forward(self, query, key=None, value=None, identity=None,
                 query_pos=None, key_padding_mask=None, reference_points=None,
-                spatial_shapes=None, level_start_index=None, **kwargs):
+                spatial_shapes=None, level_start_index=None, post_norm=None,
+                **kwargs):
         if value is None:
             value = query
         if identity is None:
@@ -227,23 +270,31 @@ class MultiScaleDeformableAttention(BaseModule):
             value = value.permute(1, 0, 2)
         bs, num_query, _ = query.shape
         _, num_value, _ = value.shape
-        value = self.value_proj(value)
+        fused = _fused_linear_on(query, self.dropout)
+        lin = _linear if fused else (lambda m, x: m(x))
+        value = lin(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
-        offsets = self.sampling_offsets(query).view(
+        offsets = lin(self.sampling_offsets, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        logits = self.attention_weights(query).view(
+        logits = lin(self.attention_weights, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] != 2:
             raise ValueError('Last dim of reference_points must be 2, but get '
                              f'{reference_points.shape[-1]} instead.')
         output = ms_deform_attn_fused(value, spatial_shapes, level_start_index,
                                       reference_points, offsets, logits)
+        if fused:
+            res = identity if self.batch_first else identity.permute(1, 0, 2)
+            output = _linear(self.output_proj, output, residual=res,
+                             norm=post_norm)
+            return output if self.batch_first else output.permute(1, 0, 2)
         output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
-        return self.dropout(output) + identity
+        output = self.dropout(output) + identity
+        return output if post_norm is None else post_norm(output)
 
 
 # ---------------------------------------------------------------------------
@@ -303,16 +354,18 @@ class DA_MSDeformableAttention(BaseModule):
     # the three input projections, shared by both execution paths
     def project_value(self, value, key_padding_mask=None):
         bs, num_value, _ = value.shape
-        value = self.value_proj(value)
+        lin = _linear if _fused_linear_on(value) else (lambda m, x: m(x))
+        value = lin(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         return value.view(bs, num_value, self.num_heads, -1)
 
     def project_query(self, query):
         bs, num_query, _ = query.shape
-        offsets = self.sampling_offsets(query).view(
+        lin = _linear if _fused_linear_on(query) else (lambda m, x: m(x))
+        offsets = lin(self.sampling_offsets, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        logits = self.attention_weights(query).view(
+        logits = lin(self.attention_weights, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if self.disable_deformable:
             offsets = offsets * 0
@@ -403,18 +456,23 @@ class DA_SpatialCrossAttention(BaseModule):
     def init_weight(self):
         _xavier_uniform(self.output_proj)
 
-    def _finish(self, slots, inp_residual):
+    def _finish(self, slots, inp_residual, post_norm=None):
+        if self.layer_scale is None and _fused_linear_on(slots, self.dropout):
+            return _linear(self.output_proj, slots, residual=inp_residual,
+                           norm=post_norm)
         slots = self.output_proj(slots)
         if self.layer_scale is None:
-            return self.dropout(slots) + inp_residual
-        return self.dropout(self.layer_scale * slots) + inp_residual
+            out = self.dropout(slots) + inp_residual
+        else:
+            out = self.dropout(self.layer_scale * slots) + inp_residual
+        return out if post_norm is None else post_norm(out)
 
     def forward(self, query, key, value, residual=None, query_pos=None,
                 key_padding_mask=None, reference_points=None,
                 spatial_shapes=None, reference_points_cam=None,
                 level_start_index=None, flag='encoder', bev_query_depth=None,
                 pred_img_depth=None, bev_mask=None, per_cam_mask_list=None,
-                **kwargs):
+                post_norm=None, **kwargs):
         """query (bs, nq, E); key/value (num_cams, n_value, bs, E);
         reference_points_cam (num_cams, bs, nq, Z, 2); bev_query_depth
         (num_cams, bs, nq, Z, 1); pred_img_depth (bs, num_cams, DC, H, W);
@@ -431,7 +489,7 @@ class DA_SpatialCrossAttention(BaseModule):
             return self._forward_rebatch(
                 query, value, inp_residual, key_padding_mask, spatial_shapes,
                 reference_points_cam, level_start_index, bev_query_depth,
-                pred_img_depth, bev_mask, per_cam_mask_list)
+                pred_img_depth, bev_mask, per_cam_mask_list, post_norm)
 
         da = self.deformable_attention
         B, N, DC, H, W = pred_img_depth.shape
@@ -447,12 +505,12 @@ class DA_SpatialCrossAttention(BaseModule):
             v, depth_prob, reference_points_cam, bev_query_depth,
             per_cam_mask_list, offsets, logits, spatial_shapes,
             level_start_index, self.dbound, da.num_Z_anchors)
-        return self._finish(slots, inp_residual)
+        return self._finish(slots, inp_residual, post_norm)
 
     def _forward_rebatch(self, query, value, inp_residual, key_padding_mask,
                          spatial_shapes, reference_points_cam,
                          level_start_index, bev_query_depth, pred_img_depth,
-                         bev_mask, per_cam_mask_list):
+                         bev_mask, per_cam_mask_list, post_norm=None):
         """The reference's per-camera re-batching algorithm (:156-216), used
         when a ``bev_mask`` restricts the queries (its empty-camera rule,
         :166-167, has no per-query formulation)."""
@@ -506,7 +564,7 @@ class DA_SpatialCrossAttention(BaseModule):
         count = seen.permute(1, 2, 0).sum(-1)
         count = torch.clamp(count, min=1.0)
         slots = slots / count[..., None]
-        return self._finish(slots, inp_residual)
+        return self._finish(slots, inp_residual, post_norm)
 
 
 # ---------------------------------------------------------------------------
@@ -616,7 +674,16 @@ class BEVFormerEncoderLayer(MyCustomBaseTransformerLayer):
                           for _ in range(self.num_attn)]
         else:
             assert len(attn_masks) == self.num_attn
-        for op in self.operation_order:
+        # a 'norm' that directly follows an attention / FFN runs in that module's
+        # last Linear (same arithmetic, one launch less and no extra pass)
+        ops = self.operation_order
+        skip_norm = False
+        for pos, op in enumerate(ops):
+            fold = None
+            if (op != 'norm' and not self.pre_norm and pos + 1 < len(ops)
+                    and ops[pos + 1] == 'norm'
+                    and isinstance(self.norms[norm_index], nn.LayerNorm)):
+                fold = self.norms[norm_index]
             if op == 'self_attn':
                 query = self.attentions[attn_index](
                     query, None, None, identity if self.pre_norm else None,
@@ -626,11 +693,14 @@ class BEVFormerEncoderLayer(MyCustomBaseTransformerLayer):
                     spatial_shapes=_const_tensor(((bev_h, bev_w),),
                                                  query.device),
                     level_start_index=_const_tensor((0,), query.device),
-                    **kwargs)
+                    post_norm=fold, **kwargs)
                 attn_index += 1
                 identity = query
+                skip_norm = fold is not None
             elif op == 'norm':
-                query = self.norms[norm_index](query)
+                if not skip_norm:
+                    query = self.norms[norm_index](query)
+                skip_norm = False
                 norm_index += 1
             elif op == 'cross_attn':
                 query = self.attentions[attn_index](
@@ -644,13 +714,17 @@ class BEVFormerEncoderLayer(MyCustomBaseTransformerLayer):
                     level_start_index=level_start_index,
                     bev_query_depth=bev_query_depth,
                     pred_img_depth=pred_img_depth, bev_mask=bev_mask,
-                    per_cam_mask_list=per_cam_mask_list, **kwargs)
+                    per_cam_mask_list=per_cam_mask_list, post_norm=fold,
+                    **kwargs)
                 attn_index += 1
                 identity = query
+                skip_norm = fold is not None
             elif op == 'ffn':
                 query = self.ffns[ffn_index](
-                    query, identity if self.pre_norm else None)
+                    query, identity if self.pre_norm else None,
+                    post_norm=fold)
                 ffn_index += 1
+                skip_norm = fold is not None
         return query
 
 

@@ -318,7 +318,8 @@ int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
  * 3xTF32 on the tensor cores (error ~1e-6 relative, inside the 1e-4 bar; plain
  * TF32 is not).  Weights are packed once (hi / lo split in the shared-memory
  * layout of the kernel) with fbbev_linear_pack into fbbev_linear_packed_bytes
- * bytes; k % 4 == 0, n % 4 == 0, n <= 160 (split wider layers over n),
+ * bytes; k % 4 == 0, n % 4 == 0, n <= 160 (split wider layers over n), n <= 80
+ * with the LayerNorm epilogue (whole rows stay in shared memory),
  * 16-byte aligned pointers; otherwise FBBEV_ERR_UNSUPPORTED /
  * FBBEV_ERR_INVALID_ARGUMENT.
  */

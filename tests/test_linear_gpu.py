@@ -31,7 +31,10 @@ CASES = [
     (4224, 80, 80, True, False, False, False),
     (777, 80, 32, False, False, False, False),
     (513, 44, 20, True, True, True, False),
-    (300, 160, 128, True, False, True, True),
+    (300, 160, 64, True, False, True, True),
+    (300, 160, 128, True, False, True, False),
+    (700, 80, 80, True, False, False, True),
+    (129, 40, 16, False, True, True, True),
 ]
 
 
