@@ -341,6 +341,13 @@ class CpuReference:
         self.cpu = cpu
         self.backward_ref = backward_ref
         self.w = w_cpu
+        # all host cores this process may use (torchrun exports
+        # OMP_NUM_THREADS=1, which would make the baseline single-threaded)
+        try:
+            n_cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_cores = os.cpu_count() or 1
+        cpu.set_num_threads(n_cores)
         self.threads = cpu.num_threads()
         torch.set_num_threads(self.threads)
         gs = [int(v) for v in w_cpu.vt.grid_size]
@@ -422,10 +429,13 @@ def main():
                     help="time eager plugin calls instead of a CUDA graph "
                          "replay of them")
     args = ap.parse_args()
-    world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
-        run_reference(args, world, rank)
+        # CPU arm: rank 0 alone works, the other ranks of a torchrun launch
+        # exit at once; no process group is needed
+        run_reference(args, int(os.environ.get("WORLD_SIZE", "1")),
+                      int(os.environ.get("RANK", "0")))
         return
+    world, rank, local = dist_setup(args.gpus)
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
     import torch.distributed as dist

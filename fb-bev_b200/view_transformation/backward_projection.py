@@ -44,6 +44,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops import linear as _linear_ops
+from .forward_projection import inv3x3_many
 from ..ops import ms_deform_attn as _msda_ops
 from ..ops.ms_deform_attn import (MultiScaleDeformableAttnFunction_fp32,
                                   da_spatial_cross_attention_core,
@@ -149,11 +150,26 @@ class CustormLearnedPositionalEncoding(BaseModule):
         nn.init.uniform_(self.col_embed.weight)
 
     def forward(self, bs, h, w, device):
+        # with gradients off the encoding is a constant of the two embedding
+        # tables: build it once per (shape, table version) instead of ~8
+        # gather / repeat / cat kernels every forward
+        key = None
+        if not torch.is_grad_enabled():
+            key = (bs, h, w, str(device), self.col_embed.weight._version,
+                   self.row_embed.weight._version,
+                   self.col_embed.weight.data_ptr(),
+                   self.row_embed.weight.data_ptr())
+            hit = self.__dict__.get('_pos_cache')
+            if hit is not None and hit[0] == key:
+                return hit[1]
         x_embed = self.col_embed(torch.arange(w, device=device))
         y_embed = self.row_embed(torch.arange(h, device=device))
         pos = torch.cat((x_embed.unsqueeze(0).repeat(h, 1, 1),
                          y_embed.unsqueeze(1).repeat(1, w, 1)), dim=-1)
-        return pos.permute(2, 0, 1).unsqueeze(0).repeat(bs, 1, 1, 1)
+        pos = pos.permute(2, 0, 1).unsqueeze(0).repeat(bs, 1, 1, 1)
+        if key is not None:
+            self.__dict__['_pos_cache'] = (key, pos)
+        return pos
 
     def __repr__(self):
         return (f'{self.__class__.__name__}(num_feats={self.num_feats}, '
@@ -808,10 +824,10 @@ class bevformer_encoder(BaseModule):
         without the host-side error check)."""
         rots, trans, intrins, post_rots, post_trans, bda = [
             t.float() for t in cam_params]
-        inv = lambda m: torch.linalg.inv_ex(m)[0]  # noqa: E731
-        ego2cam = inv(rots.matmul(inv(intrins)))
+        inv_k, inv_bda = inv3x3_many(intrins, bda)
+        ego2cam, = inv3x3_many(rots.matmul(inv_k))
         return _msda_ops.point_sampling(
-            self._axes(rots.device), inv(bda), trans, ego2cam, post_rots,
+            self._axes(rots.device), inv_bda, trans, ego2cam, post_rots,
             post_trans, self.final_dim)
 
     def point_sampling(self, reference_points, pc_range, img_metas,

@@ -33,6 +33,22 @@ __all__ = ['gen_dx_bx', 'LSSViewTransformerFunction3D',
            'LSSViewTransformerFunction']
 
 
+def inv3x3_many(*mats):
+    """Inverses of several stacks of small square matrices with ONE batched
+    ``torch.linalg.inv_ex`` call (== torch.inverse per matrix, without the
+    host-side error check and its device synchronisation).  Each inverse call
+    costs ~7 kernel launches (LU, pivots, two triangular solves), so sharing it
+    matters in a 0.7 ms step."""
+    n = mats[0].shape[-1]
+    flat = [m.reshape(-1, n, n) for m in mats]
+    inv = torch.linalg.inv_ex(torch.cat(flat, 0) if len(flat) > 1 else flat[0])[0]
+    out, o = [], 0
+    for m, f in zip(mats, flat):
+        out.append(inv[o:o + f.shape[0]].reshape(m.shape))
+        o += f.shape[0]
+    return out
+
+
 def gen_dx_bx(xbound, ybound, zbound):
     """Voxel size, first-voxel centre and voxel count per axis
     (view_transformer.py:17-21); consumed by FBOCC (fbocc.py:110, 183-188)."""
@@ -138,9 +154,10 @@ class _LSSBase(BaseModule):
         """Index straight from the camera parameters (fused geometry).  The
         two 3x3 products the reference forms before touching the points
         (view_transformer.py:483-491) are formed here by the same torch ops
-        (inv_ex == torch.inverse without the host-side error check)."""
-        inv_pr = torch.linalg.inv_ex(post_rots)[0]
-        cam2ego = rots.matmul(torch.linalg.inv_ex(cam2imgs)[0])
+        (inv_ex == torch.inverse without the host-side error check; the two
+        inverses share one batched call)."""
+        inv_pr, inv_k = inv3x3_many(post_rots, cam2imgs)
+        cam2ego = rots.matmul(inv_k)
         return voxel_pooling_prepare_from_cams(
             self._frustum_axes(rots.device), inv_pr, post_trans, cam2ego,
             trans, bda, self.D, self.grid_lower_bound, self.grid_interval,
