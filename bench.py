@@ -428,6 +428,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="time eager plugin calls instead of a CUDA graph "
                          "replay of them")
+    ap.add_argument("--eager-only", action="store_true",
+                    help="profiling aid: stop after the eager pass (what ncu "
+                         "captures) and print only its numbers")
     args = ap.parse_args()
     if args.impl == "reference":
         # CPU arm: rank 0 alone works, the other ranks of a torchrun launch
@@ -478,6 +481,13 @@ def main():
     launches = (L.fbbev_debug_launch_count() - launches0) / args.steps
     eager_ms = sum(s.elapsed_time(e) for s, e in events) / args.steps
     pool_us = ktimer.mean_us()
+    if args.eager_only:
+        if rank == 0:
+            print(json.dumps({"eager_ms_per_step": eager_ms,
+                              "pool_us": pool_us, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- headline pass: the same K steps as CUDA-graph replays --------------
     use_graph = not args.no_graph
