@@ -13,19 +13,16 @@ from .. import _lib
 MAX_N = 160  # widest column block of one launch
 
 
-class _Packed:
-    __slots__ = ("blocks", "key")
-
-
-_CACHE = {}
-
-
 def _pack(weight):
-    """hi / lo split image of `weight` (n, k), one block per <= 160 columns."""
+    """hi / lo split image of `weight` (n, k), one block per <= 160 columns.
+
+    Cached ON the weight tensor (so it dies with it and can never be mistaken
+    for another tensor's) and keyed by storage address and version counter, so
+    an optimizer step or ``load_state_dict`` triggers a re-pack."""
     key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
-    hit = _CACHE.get(id(weight))
-    if hit is not None and hit.key == key:
-        return hit.blocks
+    hit = getattr(weight, "_fbbev_packed", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
     L = _lib.lib()
     n, k = weight.shape
     w = weight.detach().contiguous().float()
@@ -37,9 +34,10 @@ def _pack(weight):
         _lib.check(L.fbbev_linear_pack(_lib.ptr(w[n0:n1]), n1 - n0, k, _lib.ptr(buf),
                                        _lib.stream_ptr(w.device)), "fbbev_linear_pack")
         blocks.append((n0, n1, buf))
-    ent = _Packed()
-    ent.blocks, ent.key = blocks, key
-    _CACHE[id(weight)] = ent
+    try:
+        weight._fbbev_packed = (key, blocks)
+    except AttributeError:  # a tensor type without a __dict__: no caching
+        pass
     return blocks
 
 
