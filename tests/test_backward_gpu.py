@@ -35,6 +35,22 @@ def test_msda_forward_vs_oracle(oracle_cpu, ch):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-5)
 
 
+def test_msda_forward_backward_only_config_full_size(oracle_cpu):
+    """BASELINE.json configs[3]: 200x200 BEV queries, 4-scale 8-head
+    MSDeformAttn (embed 256 -> 32 channels per head), full size."""
+    from fbbev_b200.ops.ms_deform_attn import ms_deform_attn_forward
+    value, shapes, lsi, loc, attw = _rand_msda(
+        11, bs=1, nq=200 * 200, heads=8, ch=32,
+        shapes=((32, 88), (16, 44), (8, 22), (4, 11)), points=4)
+    attw = attw / attw.flatten(3).sum(-1)[..., None, None]
+    want = oracle_cpu.msda_fwd(value.numpy(), shapes.numpy(), lsi.numpy(),
+                               loc.numpy(), attw.numpy())
+    got = ms_deform_attn_forward(value.to(DEV), shapes.to(DEV), lsi.to(DEV),
+                                 loc.to(DEV), attw.to(DEV), 64)
+    assert got.shape == (1, 200 * 200, 256)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=ATOL)
+
+
 def test_msda_edge_locations(oracle_cpu):
     """Locations on / outside the border, NaN and huge values: zero padding and
     the (-1, H) x (-1, W) validity window of the im2col algorithm."""

@@ -33,6 +33,8 @@ def make_case(name, batch, seed=0):
         "fbocc_200": ("fbocc_200", (256, 704), 16, 6, 80),
         "unit_128": ("unit_128", (256, 704), 4, 1, 80),
         "unit_128_c64": ("unit_128", (256, 704), 4, 1, 64),
+        # BASELINE.json configs[4]: 400x400x32 voxels, 6-cam 512x1408, D = 118
+        "fbocc_400": ("fbocc_400", (512, 1408), 16, 6, 80),
     }
     grid, inp, ds, n_cams, C = cfgs[name]
     vt = LSSViewTransformerFunction3D(synthetic.GRID_CONFIGS[grid], inp, ds)
@@ -168,7 +170,8 @@ def test_dense_pool_vs_oracle(oracle_cpu, name, batch):
     assert torch.equal(bev, got.permute(0, 1, 3, 4, 2))
 
 
-@pytest.mark.parametrize("name", ["shipped", "fbocc_200", "unit_128"])
+@pytest.mark.parametrize("name", ["shipped", "fbocc_200", "unit_128",
+                                  "fbocc_400"])
 def test_vs_reference_cuda_kernel(name):
     """Same inputs through the UNMODIFIED reference kernels (oracle/_ref)."""
     from oracle import ref_cuda
@@ -223,7 +226,8 @@ def test_backward_vs_oracle_and_reference_kernel(oracle_cpu):
 
 
 # ----------------------------------- size-independent properties, full size --
-@pytest.mark.parametrize("name,batch", [("fbocc_200", 2), ("shipped", 4)])
+@pytest.mark.parametrize("name,batch", [("fbocc_200", 2), ("shipped", 4),
+                                        ("fbocc_400", 1)])
 def test_properties_full_size(name, batch):
     from fbbev_b200.ops.bev_pool_v2 import bev_pool_v2
     vt, cam, depth, feat = make_case(name, batch)
