@@ -39,7 +39,6 @@
 
 namespace fbbev {
 
-constexpr int kPoolThreads = 256;  // dense-write CTAs
 #ifndef FBBEV_SUM_THREADS
 #define FBBEV_SUM_THREADS 128
 #endif
@@ -506,7 +505,6 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
       split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
   const int T = split_pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
-  const int64_t n_tiles = (int64_t)batch * tiles_per_b;
   if (n_intervals_max > 0) {
     count_launch();
     const unsigned grid = (unsigned)w.n_sum_ctas;

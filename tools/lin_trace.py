@@ -1,3 +1,16 @@
+"""Timeline of CTA 0 of linear_tf32_kernel (clock64 per warp role).
+
+Needs a variant build with the trace hooks compiled in:
+
+    make -C fb-bev_b200/csrc OBJDIR=../../build/var_TRACE \
+         OUT=../../build/var_TRACE/libfbbev_b200.so EXTRA=-DLIN_TRACE
+    FBBEV_LIB=$PWD/build/var_TRACE/libfbbev_b200.so python tools/lin_trace.py
+
+Tags: 1 set-up done, 100+w loads of round w issued, 200+i / 300+i stage of item
+i free / filled, 400+i MMA sees item i, 500+t accumulator of tile t committed,
+600..1000+t epilogue of tile t (wait, accumulator ready, passes done,
+normalised, stored), 2 kernel end.
+"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
