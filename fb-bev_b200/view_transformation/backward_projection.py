@@ -818,6 +818,23 @@ class bevformer_encoder(BaseModule):
                 for b in (self.x_bound, self.y_bound, self.z_bound))
         return cache[key]
 
+    def _token_major(self, bev_pos):
+        """``bev_pos`` arrives as a channel-major view of the (bs, E, h, w)
+        encoding, and every ``query + query_pos`` of the layers then runs as a
+        strided elementwise kernel (~15 us on B200 instead of ~4).  With
+        gradients off the encoding is a cached constant (same root tensor every
+        forward), so its (bs, nq, E)-contiguous copy is made once."""
+        if torch.is_grad_enabled() or bev_pos.is_contiguous():
+            return bev_pos
+        root = bev_pos._base if bev_pos._base is not None else bev_pos
+        key = (root._version, tuple(bev_pos.shape), tuple(bev_pos.stride()),
+               bev_pos.storage_offset())
+        hit = self.__dict__.get('_pos_tokens')
+        if hit is None or hit[0] is not root or hit[1] != key:
+            hit = (root, key, bev_pos.contiguous())
+            self.__dict__['_pos_tokens'] = hit
+        return hit[2]
+
     def point_sampling_fused(self, cam_params):
         """``point_sampling`` as one kernel.  The small 3x3 products are formed
         with the same torch ops as the reference (inv_ex == torch.inverse
@@ -894,7 +911,7 @@ class bevformer_encoder(BaseModule):
                     ref_3d, self.pc_range, kwargs.get('img_metas'),
                     cam_params=cam_params, gt_bboxes_3d=gt_bboxes_3d)
         bev_query = bev_query.permute(1, 0, 2)
-        bev_pos = bev_pos.permute(1, 0, 2)
+        bev_pos = self._token_major(bev_pos.permute(1, 0, 2))
         for layer in self.layers:
             output = layer(
                 bev_query, key, value, *args, bev_pos=bev_pos, ref_2d=ref_2d,

@@ -202,3 +202,31 @@ def test_backward_projection_cpu_oracle_vs_reference_golden(case):
                 pred_img_depth=torch.from_numpy(g["depth"]),
                 per_cam_mask_list=torch.from_numpy(g["per_cam_mask"]))
     np.testing.assert_allclose(o.numpy(), g["sca_out"], rtol=0, atol=2e-5)
+
+
+def test_inference_caches_follow_parameter_updates():
+    """With gradients off the plugin caches constants of the weights (the
+    positional encoding and its token-major copy).  An in-place parameter update
+    -- an optimizer step, load_state_dict -- must invalidate them."""
+    import copy
+    from bp_common import build_bp, cam_params
+    from oracle import backward_ref
+    g, bp = build_bp("b_bp_e80_1lvl")
+    feats = [torch.from_numpy(g[f"feat{i}"])
+             for i in range(len(g["level_shapes"]))]
+    args = (feats, torch.from_numpy(g["lss_bev"]), cam_params(g),
+            torch.from_numpy(g["depth"]))
+    first = backward_ref.backward_projection_cpu(bp, *args)
+    again = backward_ref.backward_projection_cpu(bp, *args)   # served by caches
+    assert torch.equal(first, again)
+    with torch.no_grad():
+        bp.positional_encoding.row_embed.weight.add_(0.25)
+        bp.positional_encoding.col_embed.weight.mul_(0.5)
+    fresh = copy.deepcopy(bp)
+    for m in fresh.modules():                                  # drop every cache
+        for k in [k for k in m.__dict__ if k.startswith('_pos')]:
+            del m.__dict__[k]
+    want = backward_ref.backward_projection_cpu(fresh, *args)
+    got = backward_ref.backward_projection_cpu(bp, *args)
+    assert not torch.equal(first, got)
+    assert torch.equal(got, want)
