@@ -55,6 +55,8 @@ _SIGNATURES = {
     "fbbev_da_sca_fwd": (ctypes.c_int, [_p] * 10 + [_i32] * 10 + [_p, _p]),
     "fbbev_linear_packed_bytes": (ctypes.c_size_t, [_i32, _i32]),
     "fbbev_linear_pack": (ctypes.c_int, [_p, _i32, _i32, _p, _p]),
+    "fbbev_linear_fwd_split": (ctypes.c_int, [
+        _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "fbbev_linear_fwd": (ctypes.c_int, [
         _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i32,
         ctypes.c_float, _p, _i64, _p]),

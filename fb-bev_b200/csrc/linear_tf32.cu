@@ -42,7 +42,7 @@ constexpr int kTileM = 128;
 constexpr int kAPart = kTileM * kKB * 4;         // bytes of A_hi (== A_lo)
 constexpr int kAChunkStride = (kTileM / 8) * 128;  // bytes between K chunks
 constexpr int kLinThreads = 448;  // 14 warps, see the role table above
-constexpr int kMaxN = 160;
+constexpr int kMaxN = 192;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 232448 - 1024;
 constexpr int kSlabPitch = 20;  // floats: 16 columns + 4 (bank spread)
@@ -201,6 +201,10 @@ struct LinearParams {
   int M, K, N, npad, n_kb, relu, rows_per_cta, stages;
   int slab_pitch;  // floats per slab row: 20 (16-column chunks) or N + 4 (whole rows)
   int64_t ldx, ldr, ldy;  // row strides in floats
+  // optional second output: columns [n_split, N) go to y2 (row stride ldy2)
+  float* y2;
+  int64_t ldy2;
+  int n_split;
   float eps;
 };
 
@@ -567,9 +571,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = crow + 32 * i;
-            if (row0 + r < row_end && col < N)
-              *reinterpret_cast<float4*>(p.y + (size_t)(row0 + r) * p.ldy + col) =
+            if (row0 + r < row_end && col < N) {
+              float* dst = col < p.n_split
+                               ? p.y + (size_t)(row0 + r) * p.ldy + col
+                               : p.y2 + (size_t)(row0 + r) * p.ldy2 + (col - p.n_split);
+              *reinterpret_cast<float4*>(dst) =
                   *reinterpret_cast<const float4*>(slab + (size_t)r * pitch + 4 * cq);
+            }
           }
           group_sync();
         }
@@ -650,20 +658,24 @@ FBBEV_API int fbbev_linear_pack(const float* weight, int32_t n, int32_t k,
   return launch_status();
 }
 
-FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
-                               const float* bias, const float* residual,
-                               int64_t ldr, const float* ln_weight,
-                               const float* ln_bias, int64_t m, int32_t k,
-                               int32_t n, int32_t relu, float ln_eps, float* y,
-                               int64_t ldy, fbbev_stream_t stream) {
+static int linear_run(const float* x, int64_t ldx, const float* packed,
+                      const float* bias, const float* residual, int64_t ldr,
+                      const float* ln_weight, const float* ln_bias, int64_t m,
+                      int32_t k, int32_t n, int32_t relu, float ln_eps, float* y,
+                      int64_t ldy, float* y2, int64_t ldy2, int32_t n_split,
+                      fbbev_stream_t stream) {
   if (!x || !packed || !y || m < 0 || k <= 0 || n <= 0)
     return FBBEV_ERR_INVALID_ARGUMENT;
   if ((ln_weight == nullptr) != (ln_bias == nullptr))
     return FBBEV_ERR_INVALID_ARGUMENT;
   if (k % 4 != 0 || n % 4 != 0 || n > kMaxN || m > (int64_t)1 << 30)
     return FBBEV_ERR_UNSUPPORTED;
-  if (ldx < k || ldy < n || (residual && ldr < n) || ldx % 4 || ldy % 4 ||
+  if (ldx < k || ldy < n_split || (residual && ldr < n) || ldx % 4 || ldy % 4 ||
       (residual && ldr % 4))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (n_split < n &&
+      (!y2 || n_split <= 0 || n_split % 4 || ldy2 < n - n_split || ldy2 % 4 ||
+       ln_weight || (reinterpret_cast<uintptr_t>(y2) & 15)))
     return FBBEV_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
        reinterpret_cast<uintptr_t>(packed) |
@@ -673,6 +685,7 @@ FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
   LinearParams p;
   p.x = x; p.wp = packed; p.bias = bias; p.residual = residual;
   p.gamma = ln_weight; p.beta = ln_bias; p.y = y;
+  p.y2 = y2; p.ldy2 = ldy2; p.n_split = n_split;
   p.M = (int)m; p.K = k; p.N = n; p.npad = pad16(n); p.n_kb = n_kblocks(k);
   p.relu = relu; p.eps = ln_eps;
   p.ldx = ldx; p.ldr = ldr; p.ldy = ldy;
@@ -709,4 +722,24 @@ FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
   cudaStream_t st = as_stream(stream);
   count_launch();
   return launch_linear(p, ln, smem, grid, st);
+}
+
+FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
+                               const float* bias, const float* residual,
+                               int64_t ldr, const float* ln_weight,
+                               const float* ln_bias, int64_t m, int32_t k,
+                               int32_t n, int32_t relu, float ln_eps, float* y,
+                               int64_t ldy, fbbev_stream_t stream) {
+  return linear_run(x, ldx, packed, bias, residual, ldr, ln_weight, ln_bias, m, k,
+                    n, relu, ln_eps, y, ldy, nullptr, 0, n, stream);
+}
+
+FBBEV_API int fbbev_linear_fwd_split(const float* x, int64_t ldx,
+                                     const float* packed, const float* bias,
+                                     int64_t m, int32_t k, int32_t n,
+                                     int32_t n_split, int32_t relu, float* y0,
+                                     int64_t ldy0, float* y1, int64_t ldy1,
+                                     fbbev_stream_t stream) {
+  return linear_run(x, ldx, packed, bias, nullptr, 0, nullptr, nullptr, m, k, n,
+                    relu, 0.f, y0, ldy0, y1, ldy1, n_split, stream);
 }

@@ -10,11 +10,11 @@ import torch
 
 from .. import _lib
 
-MAX_N = 160  # widest column block of one launch
+MAX_N = 192  # widest column block of one launch
 
 
 def _pack(weight):
-    """hi / lo split image of `weight` (n, k), one block per <= 160 columns.
+    """hi / lo split image of `weight` (n, k), one block per <= MAX_N columns.
 
     Cached ON the weight tensor (so it dies with it and can never be mistaken
     for another tensor's) and keyed by storage address and version counter, so
@@ -89,3 +89,41 @@ def linear_fused(x, weight, bias=None, relu=False, residual=None, ln_weight=None
             m, k, n1 - n0, int(bool(relu)), float(eps),
             _lib.ptr(y[:, n0:n1]), y.stride(0), sp), "fbbev_linear_fwd")
     return y.view(*lead, n)
+
+
+def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache):
+    """``(x @ weight_a.T + bias_a, x @ weight_b.T + bias_b)`` as ONE launch when
+    both fit a column block (sampling_offsets + attention_weights of an
+    attention module: same input, one consumer kernel).
+
+    ``cache`` is a dict owned by the calling module; it keeps the concatenated
+    weight / bias, keyed by the parameters' storage and version counters."""
+    _lib.require_cuda(x)
+    na, k = weight_a.shape
+    nb = weight_b.shape[0]
+    if na + nb > MAX_N or na % 4 or nb % 4 or (bias_a is None) != (bias_b is None):
+        return (linear_fused(x, weight_a, bias_a), linear_fused(x, weight_b, bias_b))
+    key = tuple((t.data_ptr(), t._version) for t in
+                (weight_a, weight_b, bias_a, bias_b) if t is not None)
+    hit = cache.get("pair")
+    if hit is None or hit[0] != key:
+        w = torch.cat((weight_a.detach(), weight_b.detach()), 0).float().contiguous()
+        b = None if bias_a is None else torch.cat(
+            (bias_a.detach(), bias_b.detach()), 0).float().contiguous()
+        hit = (key, w, b)
+        cache["pair"] = hit
+    _, w, b = hit
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(-1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    m = x2.shape[0]
+    ya = torch.empty((m, na), dtype=torch.float32, device=x.device)
+    yb = torch.empty((m, nb), dtype=torch.float32, device=x.device)
+    (_, _, buf), = _pack(w)
+    L = _lib.lib()
+    _lib.check(L.fbbev_linear_fwd_split(
+        _lib.ptr(x2), x2.stride(0), _lib.ptr(buf), _lib.ptr(b), m, k, na + nb, na,
+        0, _lib.ptr(ya), na, _lib.ptr(yb), nb, _lib.stream_ptr(x.device)),
+        "fbbev_linear_fwd_split")
+    return ya.view(*lead, na), yb.view(*lead, nb)

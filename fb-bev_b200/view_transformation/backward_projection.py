@@ -106,6 +106,17 @@ def _linear(mod, x, relu=False, residual=None, norm=None):
         eps=1e-5 if norm is None else norm.eps)
 
 
+def _linear_pair(owner, mod_a, mod_b, x):
+    """``(mod_a(x), mod_b(x))`` for two nn.Linears on the same input, one launch
+    when their widths allow; set ``FBBEV_LINEAR_PAIR=0`` for two launches."""
+    if (os.environ.get('FBBEV_LINEAR_PAIR', '1') == '1'
+            and mod_a.weight.shape[1] % 4 == 0):
+        return _linear_ops.linear_pair(
+            x, mod_a.weight, mod_a.bias, mod_b.weight, mod_b.bias,
+            owner.__dict__.setdefault('_pair_cache', {}))
+    return _linear(mod_a, x), _linear(mod_b, x)
+
+
 def _xavier_uniform(module, bias=0.):
     if getattr(module, 'weight', None) is not None:
         nn.init.xavier_uniform_(module.weight)
@@ -292,9 +303,15 @@ class MultiScaleDeformableAttention(BaseModule):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
-        offsets = lin(self.sampling_offsets, query).view(
+        if fused:
+            offsets, logits = _linear_pair(self, self.sampling_offsets,
+                                           self.attention_weights, query)
+        else:
+            offsets = self.sampling_offsets(query)
+            logits = self.attention_weights(query)
+        offsets = offsets.view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        logits = lin(self.attention_weights, query).view(
+        logits = logits.view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] != 2:
             raise ValueError('Last dim of reference_points must be 2, but get '
@@ -378,10 +395,15 @@ class DA_MSDeformableAttention(BaseModule):
 
     def project_query(self, query):
         bs, num_query, _ = query.shape
-        lin = _linear if _fused_linear_on(query) else (lambda m, x: m(x))
-        offsets = lin(self.sampling_offsets, query).view(
+        if _fused_linear_on(query):
+            offsets, logits = _linear_pair(self, self.sampling_offsets,
+                                           self.attention_weights, query)
+        else:
+            offsets = self.sampling_offsets(query)
+            logits = self.attention_weights(query)
+        offsets = offsets.view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        logits = lin(self.attention_weights, query).view(
+        logits = logits.view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if self.disable_deformable:
             offsets = offsets * 0

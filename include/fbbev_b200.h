@@ -318,7 +318,7 @@ int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
  * 3xTF32 on the tensor cores (error ~1e-6 relative, inside the 1e-4 bar; plain
  * TF32 is not).  Weights are packed once (hi / lo split in the shared-memory
  * layout of the kernel) with fbbev_linear_pack into fbbev_linear_packed_bytes
- * bytes; k % 4 == 0, n % 4 == 0, n <= 160 (split wider layers over n), n <= 80
+ * bytes; k % 4 == 0, n % 4 == 0, n <= 192 (split wider layers over n), n <= 80
  * with the LayerNorm epilogue (whole rows stay in shared memory),
  * 16-byte aligned pointers; otherwise FBBEV_ERR_UNSUPPORTED /
  * FBBEV_ERR_INVALID_ARGUMENT.
@@ -331,6 +331,18 @@ int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
                      const float* ln_weight, const float* ln_bias, int64_t m,
                      int32_t k, int32_t n, int32_t relu, float ln_eps, float* y,
                      int64_t ldy, fbbev_stream_t stream);
+
+/* Two Linears that read the same x as ONE launch: `packed` / `bias` hold the
+ * row-concatenated weight (n = n0 + n1 rows, n <= 192) and bias; output columns
+ * [0, n_split) go to y0 (row stride ldy0), [n_split, n) to y1 (ldy1), each dense.
+ * This is sampling_offsets + attention_weights of both attention modules
+ * (spatial_cross_attention_depth.py:420-424, 533-540): they act on the same
+ * query and feed one sampling kernel.  No residual / LayerNorm here. */
+int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* packed,
+                           const float* bias, int64_t m, int32_t k, int32_t n,
+                           int32_t n_split, int32_t relu, float* y0,
+                           int64_t ldy0, float* y1, int64_t ldy1,
+                           fbbev_stream_t stream);
 
 #ifdef __cplusplus
 }

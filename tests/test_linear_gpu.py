@@ -80,3 +80,48 @@ def test_strided_views_and_batch_dims():
     ref = F.linear(x.double(), w.double())
     assert y.shape == (2, 500, 80)
     assert (y.double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("m,k,na,nb", [(40000, 80, 128, 64), (40000, 80, 64, 32),
+                                       (513, 80, 128, 64), (300, 44, 8, 12),
+                                       (1000, 80, 160, 64)])
+def test_linear_pair_one_launch(m, k, na, nb):
+    """sampling_offsets + attention_weights as one launch with two outputs
+    (fbbev_linear_fwd_split); wider pairs fall back to two launches."""
+    from fbbev_b200.ops.linear import linear_pair
+    g = torch.Generator(device="cuda").manual_seed(m + na)
+    x = torch.randn(m, k, device="cuda", generator=g)
+    wa = torch.randn(na, k, device="cuda", generator=g) / k ** 0.5
+    wb = torch.randn(nb, k, device="cuda", generator=g) / k ** 0.5
+    ba = torch.randn(na, device="cuda", generator=g)
+    bb = torch.randn(nb, device="cuda", generator=g)
+    cache = {}
+    with torch.no_grad():
+        ya, yb = linear_pair(x, wa, ba, wb, bb, cache)
+        ya2, yb2 = linear_pair(x, wa, ba, wb, bb, cache)      # cached weights
+    assert ya.shape == (m, na) and yb.shape == (m, nb)
+    assert ya.is_contiguous() and yb.is_contiguous()
+    assert (ya.double() - F.linear(x.double(), wa.double(), ba.double())
+            ).abs().max().item() < 2e-5
+    assert (yb.double() - F.linear(x.double(), wb.double(), bb.double())
+            ).abs().max().item() < 2e-5
+    assert torch.equal(ya, ya2) and torch.equal(yb, yb2)
+    wb.mul_(2.0)                                               # version bump -> re-pack
+    with torch.no_grad():
+        _, yb3 = linear_pair(x, wa, ba, wb, bb, cache)
+    assert (yb3.double() - F.linear(x.double(), wb.double(), bb.double())
+            ).abs().max().item() < 4e-5
+
+
+def test_linear_widest_block():
+    """n = 192 (the widest single launch) and n = 320 as 192 + 128."""
+    from fbbev_b200.ops.linear import linear_fused
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(3000, 80, device="cuda", generator=g)
+    for n in (192, 320):
+        w = torch.randn(n, 80, device="cuda", generator=g) / 9
+        b = torch.randn(n, device="cuda", generator=g)
+        with torch.no_grad():
+            y = linear_fused(x, w, b, relu=True)
+        ref = F.linear(x.double(), w.double(), b.double()).relu()
+        assert (y.double() - ref).abs().max().item() < 2e-5
