@@ -23,13 +23,15 @@
 //               K-major layout (8x16-byte core matrices, no swizzle);
 //   warp  13    one lane starts the 1-D bulk copy (TMA) of the pre-packed weight
 //               block of a stage as soon as the stage is free;
-//   warp  12    one lane issues the MMAs (M=128, N<=160, K=8 per instruction),
+//   warp  12    one lane issues the MMAs (M=128, N<=192, K=8 per instruction),
 //               tcgen05.commit releases the stage / publishes the accumulator;
 //   warps 0-3, 8-11  two epilogue groups, one per TMEM accumulator (even / odd
 //               tiles): tcgen05.ld (lane == row), bias / ReLU / residual /
-//               LayerNorm in registers, row stores.  The epilogue is the
-//               longest stage per tile (ncu: one warp per scheduler, dependent
-//               issue), hence two groups.
+//               LayerNorm, rows staged through a shared-memory slab so that
+//               global loads and stores are coalesced (optionally two outputs:
+//               a column split, for two Linears that share their input).  The
+//               epilogue is the longest stage per tile (one warp per scheduler,
+//               dependent issue), hence two groups.
 //   Ring of K-blocks of 40 floats (5 k-steps) between loaders and MMA, two
 //   accumulators in TMEM between MMA and epilogue.
 #include "common.cuh"
