@@ -78,3 +78,46 @@ def test_layer_injects_batch_first_and_builds_from_config():
     assert layer.operation_order[0] == 'self_attn' and not layer.pre_norm
     assert len(layer.norms) == 3 and len(layer.ffns) == 1
     assert layer.ffns[0].layers[0][0].out_features == 4 * int(g["E"])
+
+
+def test_linear_host_decisions():
+    """Host-side rules of the tensor-core Linear path (no GPU needed): which
+    LayerNorm widths fit, and that CPU tensors / autograd keep the torch path."""
+    import torch.nn as nn
+    from fbbev_b200.ops import linear as lin
+    from fbbev_b200.view_transformation import backward_projection as bp
+    assert lin.MAX_N == 192
+    assert [n for n in range(16, 193, 16) if lin.ln_supported(n)] == \
+        [16, 32, 48, 64, 80]
+    x = torch.randn(7, 80)
+    assert not bp._fused_linear_on(x)                      # CPU tensor
+    with torch.no_grad():
+        assert not bp._fused_linear_on(x)                  # still CPU
+    fc, norm = nn.Linear(80, 80), nn.LayerNorm(80)
+    res = torch.randn(7, 80)
+    # folding the norm into the producer is the same arithmetic as the
+    # reference's op order (here through the torch path)
+    ffn = bp.FFN(embed_dims=80, feedforward_channels=160, ffn_drop=0.0)
+    want = norm(ffn(x, res))
+    got = ffn(x, res, post_norm=norm)
+    assert torch.equal(got, want)
+    with pytest.raises(Exception):
+        lin.linear_fused(x, fc.weight, fc.bias)            # no CPU fallback
+
+
+def test_token_major_positional_encoding_cache():
+    from fbbev_b200.view_transformation.backward_projection import \
+        bevformer_encoder
+    enc = bevformer_encoder.__new__(bevformer_encoder)
+    enc.__dict__.update({'_parameters': {}, '_modules': {}, '_buffers': {}})
+    root = torch.randn(1, 8, 4, 5)
+    view = root.flatten(2).permute(2, 0, 1).permute(1, 0, 2)   # (bs, nq, E)
+    assert not view.is_contiguous()
+    assert enc._token_major(view) is view                      # autograd on
+    with torch.no_grad():
+        a = enc._token_major(view)
+        b = enc._token_major(root.flatten(2).permute(2, 0, 1).permute(1, 0, 2))
+        assert a.is_contiguous() and torch.equal(a, view) and a is b
+        root.mul_(2.0)                                         # version bump
+        c = enc._token_major(root.flatten(2).permute(2, 0, 1).permute(1, 0, 2))
+        assert c is not a and torch.equal(c, view)

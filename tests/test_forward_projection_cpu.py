@@ -56,3 +56,19 @@ def test_grid_size_float32_quirk():
     vt = LSSViewTransformerFunction3D(GRID_CONFIGS["fbocc_200"], (256, 704),
                                       16)
     assert [int(v) for v in vt.grid_size] == [200, 200, 16]
+
+
+def test_inv3x3_many_equals_per_matrix_inverse():
+    """One batched inverse call for several stacks == torch.inverse on each
+    (the fused-geometry host code shares the call)."""
+    from fbbev_b200.view_transformation.forward_projection import inv3x3_many
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(2, 6, 3, 3, generator=g) + 3 * torch.eye(3)
+    b = torch.randn(2, 3, 3, generator=g) + 3 * torch.eye(3)
+    c = torch.randn(5, 3, 3, generator=g) + 3 * torch.eye(3)
+    ia, ib, ic = inv3x3_many(a, b, c)
+    assert ia.shape == a.shape and ib.shape == b.shape and ic.shape == c.shape
+    for got, m in ((ia, a), (ib, b), (ic, c)):
+        assert torch.equal(got, torch.inverse(m))
+    only, = inv3x3_many(a)
+    assert torch.equal(only, torch.inverse(a))
