@@ -386,170 +386,6 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
   }
 }
 
-// ------------------- K2', persistent and double-buffered -------------------
-// Same tile arithmetic as dense_write_kernel, but a CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... and copies the NEXT tile's interval
-// rows and index words (cp.async, second buffer) while it streams the current
-// tile out, so the two dependent memory levels of a tile (tile table -> rows /
-// index words) no longer sit in front of its store phase.
-// smem: 2 x { rows[T][c + 4] | seg_rank[T] ist[T] iln[T] } | zero row[c + 4]
-//       | slot[T] carry_lo[T] carry_n[T]
-__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
-  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc)
-               : "memory");
-}
-
-template <int T>
-__global__ void __launch_bounds__(2 * T) dense_write_stream_kernel(
-    const float* __restrict__ V, const float* __restrict__ X,
-    const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
-    const int* __restrict__ interval_starts,
-    const int* __restrict__ interval_lengths, int c, int zyx, int tiles_per_b,
-    int n_tiles, float* __restrict__ out) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int kWrThreads = 2 * T, kWrWarps = kWrThreads / kWarp;
-  const int pitch = c + 4;
-  const size_t buf_floats = (size_t)T * pitch + 3 * T;  // rows + 3 index arrays
-  float* base = reinterpret_cast<float*>(smem_raw);
-  float* zrow = base + 2 * buf_floats;
-  int* slot = reinterpret_cast<int*>(zrow + pitch);
-  int* carry_lo = slot + T;
-  int* carry_n = carry_lo + T;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c4 = c >> 2;
-  constexpr int LPR = T / 4, RPW = kWarp / LPR;
-  const int g = lane % LPR;
-  const int row0 = warp * RPW + lane / LPR;
-  const int64_t step = (int64_t)kWrWarps * RPW * zyx;
-  const int G = gridDim.x;
-
-  // copy the interval rows and index words of tile `first..last` into buffer b
-  auto issue = [&](int first, int last, int b) {
-    const int nrows = min(last - first, T);
-    float* rows = base + b * buf_floats;
-    int* idx = reinterpret_cast<int*>(rows + (size_t)T * pitch);
-    const float4* src = reinterpret_cast<const float4*>(V) + (int64_t)first * c4;
-    for (int r = warp; r < nrows; r += kWrWarps)
-      for (int v = lane; v < c4; v += kWarp)
-        cp_async16(rows + (size_t)r * pitch + 4 * v, src + (size_t)r * c4 + v);
-    for (int r = tid; r < nrows; r += kWrThreads) {
-      cp_async4(idx + r, seg_rank + first + r);
-      cp_async4(idx + T + r, interval_starts + first + r);
-      cp_async4(idx + 2 * T + r, interval_lengths + first + r);
-    }
-  };
-
-  int t = blockIdx.x;
-  if (t >= n_tiles) return;
-  for (int q = tid; q < pitch; q += kWrThreads) zrow[q] = 0.f;
-  int i0 = __ldg(tile_first + t), i1 = __ldg(tile_first + t + 1);
-  issue(i0, i1, 0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  int tn = t + G, j0 = 0, j1 = 0;
-  if (tn < n_tiles) {
-    j0 = __ldg(tile_first + tn);
-    j1 = __ldg(tile_first + tn + 1);
-  }
-  int cur = 0;
-  while (true) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // tile t has landed; nobody reads the other buffer any more
-    const int tnn = tn + G;
-    int k0 = 0, k1 = 0;
-    if (tn < n_tiles) {
-      issue(j0, j1, cur ^ 1);
-      if (tnn < n_tiles) {
-        k0 = __ldg(tile_first + tnn);
-        k1 = __ldg(tile_first + tnn + 1);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-
-    // ---- stream tile t out of buffer `cur`
-    const int b = t / tiles_per_b;
-    const int v0 = (t - b * tiles_per_b) * T;
-    const int nv = min(T, zyx - v0);
-    const int nrows = min(i1 - i0, T);
-    float* o = out + ((int64_t)b * c + row0) * zyx + v0 + 4 * g;
-    if (nrows <= 0) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (4 * g < nv)
-        for (int row = row0; row < c; row += kWrWarps * RPW, o += step)
-          st_stream(reinterpret_cast<float4*>(o), z);
-    } else {
-      float* rows = base + cur * buf_floats;
-      const int* idx = reinterpret_cast<const int*>(rows + (size_t)T * pitch);
-      for (int q = tid; q < T; q += kWrThreads) slot[q] = T;
-      __syncthreads();
-      const int64_t rank0 = (int64_t)b * zyx + v0;
-      int any_carry = 0;
-      for (int r = tid; r < nrows; r += kWrThreads) {
-        const int64_t vl = (int64_t)idx[r] - rank0;
-        if (vl >= 0 && vl < nv) slot[vl] = r;
-        const int st = idx[T + r], ln = idx[2 * T + r];
-        const int lo = st / kPtsPerWarp;
-        const int nx = (st + ln - 1) / kPtsPerWarp - lo;
-        carry_lo[r] = lo;
-        carry_n[r] = nx;
-        any_carry |= nx > 0;
-      }
-      if (__syncthreads_or(any_carry)) {
-        const float4* X4 = reinterpret_cast<const float4*>(X);
-        for (int r = warp; r < nrows; r += kWrWarps) {
-          const int nx = carry_n[r];
-          if (nx == 0) continue;
-          for (int v = lane; v < c4; v += kWarp) {
-            float4* dst = reinterpret_cast<float4*>(rows + (size_t)r * pitch + 4 * v);
-            float4 a = *dst;
-            const float4* src = X4 + (int64_t)(carry_lo[r] + 1) * c4 + v;
-            for (int k = 0; k < nx; k += 4) {
-              float4 tt[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                tt[j] = (k + j < nx) ? __ldcg(src + (int64_t)(k + j) * c4)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (k + j < nx) {
-                  a.x += tt[j].x; a.y += tt[j].y; a.z += tt[j].z; a.w += tt[j].w;
-                }
-            }
-            *dst = a;
-          }
-        }
-        __syncthreads();
-      }
-      if (4 * g < nv) {
-        const int4 s4 = *reinterpret_cast<const int4*>(slot + 4 * g);
-        const float* rx = s4.x == T ? zrow : rows + (size_t)s4.x * pitch;
-        const float* ry = s4.y == T ? zrow : rows + (size_t)s4.y * pitch;
-        const float* rz = s4.z == T ? zrow : rows + (size_t)s4.z * pitch;
-        const float* rw = s4.w == T ? zrow : rows + (size_t)s4.w * pitch;
-#pragma unroll 5
-        for (int row = row0; row < c; row += kWrWarps * RPW, o += step) {
-          float4 v;
-          v.x = rx[row];
-          v.y = ry[row];
-          v.z = rz[row];
-          v.w = rw[row];
-          st_stream(reinterpret_cast<float4*>(o), v);
-        }
-      }
-    }
-    if (tn >= n_tiles) break;
-    t = tn; i0 = j0; i1 = j1;
-    tn = tnn; j0 = k0; j1 = k1;
-    cur ^= 1;
-  }
-}
-
-static inline size_t stream_smem_bytes(int T, int c) {
-  return 2 * ((size_t)T * (c + 4) * 4 + (size_t)3 * T * 4) + (size_t)(c + 4) * 4 +
-         (size_t)3 * T * 4;
-}
-
 static inline size_t write_smem_bytes(int T, int c) {
   return (size_t)(T + 1) * (c + 4) * 4 + (size_t)3 * T * 4;
 }
@@ -659,45 +495,6 @@ static int launch_write(const SplitWs& w, const int* interval_starts,
   return launch_status();
 }
 
-// FBBEV_POOL_STREAM=1 selects the persistent double-buffered dense write.
-static bool use_stream_writer() {
-  static const char* env = getenv("FBBEV_POOL_STREAM");
-  return env && atoi(env) == 1;
-}
-
-template <int T>
-static int launch_write_stream(const SplitWs& w, const int* interval_starts,
-                               const int* interval_lengths, int c, int64_t zyx,
-                               int tiles_per_b, int batch, float* out,
-                               cudaStream_t st) {
-  const size_t smem = stream_smem_bytes(T, c);
-  auto k = dense_write_stream_kernel<T>;
-  static int ctas_per_sm = 0, n_sm = 0;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(
-          k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-    }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, k, 2 * T, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (ctas_per_sm < 1) return FBBEV_ERR_UNSUPPORTED;
-    smem_set = smem;
-  }
-  const int64_t n_tiles = (int64_t)batch * tiles_per_b;
-  const int64_t slots = (int64_t)n_sm * ctas_per_sm;
-  const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
-  k<<<grid, 2 * T, smem, st>>>(w.V, w.X, w.tile_first, w.seg_rank,
-                               interval_starts, interval_lengths, c, (int)zyx,
-                               tiles_per_b, (int)n_tiles, out);
-  return launch_status();
-}
-
 int split_launch(const float* depth, const float* feat, const int* ranks_depth,
                  const int* ranks_feat, const int* ranks_bev,
                  const int* interval_starts, const int* interval_lengths,
@@ -730,20 +527,6 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
     if (rc) return rc;
   }
   count_launch();
-  if (use_stream_writer() && stream_smem_bytes(T, c) <= 200 * 1024 &&
-      (int64_t)batch * tiles_per_b < (1ll << 31)) {
-    switch (T) {
-      case 128:
-        return launch_write_stream<128>(w, interval_starts, interval_lengths, c,
-                                        zyx, tiles_per_b, batch, out, st);
-      case 64:
-        return launch_write_stream<64>(w, interval_starts, interval_lengths, c,
-                                       zyx, tiles_per_b, batch, out, st);
-      default:
-        return launch_write_stream<32>(w, interval_starts, interval_lengths, c,
-                                       zyx, tiles_per_b, batch, out, st);
-    }
-  }
   switch (T) {
     case 128:
       return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
