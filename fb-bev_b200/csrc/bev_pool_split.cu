@@ -120,6 +120,22 @@ __global__ void split_plan_kernel(
   }
 }
 
+#ifdef POOL_TRACE
+// -DPOOL_TRACE: timeline of lane 0 / warp 0 of two CTAs of interval_sums_kernel
+// (the first one and one of the last wave), read back with
+// fbbev_debug_pool_trace (tools/pool_trace.py).  `dep` ties the clock read to
+// the value it follows, so a tag is taken when that value has arrived.
+__device__ long long g_pool_trace[2][16];
+__device__ __forceinline__ void pool_trace(int slot, int tag, unsigned dep) {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+  if (slot >= 0 && (threadIdx.x == 0) && tag < 16) g_pool_trace[slot][tag] = t;
+}
+#define PTRACE(tag, dep) pool_trace(trace_slot, tag, (unsigned)(dep))
+#else
+#define PTRACE(tag, dep) do {} while (0)
+#endif
+
 // --------------------------- K1: interval sums -----------------------------
 // Warp w folds exactly the 32 kept points [32w, 32w+32): perfectly balanced, so
 // the dense voxels next to a camera (up to 63 points each on the 200x200x16
@@ -153,7 +169,12 @@ __global__ void __launch_bounds__(kSumThreads, FBBEV_SUM_MINB)
   __shared__ float4 s_head[WPC][GPW][LG * VPL];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int64_t w = (int64_t)blockIdx.x * WPC + wi;
+#ifdef POOL_TRACE
+  const int trace_slot = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 8 ? 1 : -1);
+#endif
+  PTRACE(0, 0);
   if (w >= meta[2]) return;
+  PTRACE(1, meta[2]);
   const int n = meta[0];
   const int base = (int)w * kPtsPerWarp;
   const int cnt = min(kPtsPerWarp, meta[1] - base);
@@ -165,11 +186,14 @@ __global__ void __launch_bounds__(kSumThreads, FBBEV_SUM_MINB)
     rfL = __ldg(ranks_feat + base + lane);
     dL = __ldg(depth + __ldg(ranks_depth + base + lane));
   }
+  PTRACE(2, rbL ^ rfL ^ lb);
+  PTRACE(3, __float_as_uint(dL));
   // does the slice begin inside an interval that started earlier?
   const int carry = !(lb < n && __ldg(interval_starts + lb) == base);
   const int prev = __shfl_up_sync(kFull, rbL, 1);
   const unsigned starts =
       __ballot_sync(kFull, lane < cnt && (lane == 0 || rbL != prev));
+  PTRACE(4, starts ^ carry);
 
   const int gl = lane % LG, g = lane / LG, p0 = g * LG;
   const int c4 = c >> 2;
@@ -248,10 +272,12 @@ __global__ void __launch_bounds__(kSumThreads, FBBEV_SUM_MINB)
         acc[q].w = fmaf(xb[q].w, db, acc[q].w);
       }
     }
+    PTRACE(5 + k / 2, __float_as_uint(acc[0].x));  // batch k / 2 folded
   }
   // the run that reaches the end of the group
   if (head) flush();  // the whole group continues an earlier run
   if (GPW > 1) __syncwarp();
+  PTRACE(13, 0);
   if (!head && p0 < cnt) {
     for (int h = g + 1; h < GPW; ++h) {
       const int ph = h * LG;
@@ -267,6 +293,7 @@ __global__ void __launch_bounds__(kSumThreads, FBBEV_SUM_MINB)
     }
     flush();
   }
+  PTRACE(14, 0);
 }
 
 // ---------------------------- K2: dense write ------------------------------
@@ -541,3 +568,10 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
 }
 
 }  // namespace fbbev
+
+#ifdef POOL_TRACE
+FBBEV_API int fbbev_debug_pool_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fbbev::g_pool_trace,
+                                   sizeof(long long) * 32);
+}
+#endif
