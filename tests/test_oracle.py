@@ -230,3 +230,49 @@ def test_inference_caches_follow_parameter_updates():
     got = backward_ref.backward_projection_cpu(bp, *args)
     assert not torch.equal(first, got)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_prepare_oracle_vs_numpy_restatement_ragged(oracle_cpu, seed):
+    """The C restatement of voxel_pooling_prepare_v2 against an independent
+    numpy restatement of the same reference lines (view_transformer.py:563-605)
+    on ragged random frustums: whole cameras outside the grid, points on cell
+    faces, coordinates in (-1, 0), a batch element with nothing kept."""
+    rng = np.random.default_rng(seed)
+    B, N, D, H, W = 2 + seed % 2, 1 + seed % 3, 3 + seed, 2 + seed % 4, 5
+    lo = np.array([-4.0, -3.0, -1.0], np.float32)
+    iv = np.array([0.5, 0.75, 1.0], np.float32)
+    gs = np.array([16, 8, 3], np.float32)
+    coor = (rng.random((B, N, D, H, W, 3), dtype=np.float32) * 14 - 6).astype(
+        np.float32)
+    coor[..., ::2, :, 0] = np.round(coor[..., ::2, :, 0] * 2) / 2   # on faces
+    coor[0, 0] += 100.0                                             # camera out
+    if B > 2:
+        coor[2] -= 100.0                                            # empty frame
+    got = oracle_cpu.voxel_prepare(coor, lo, iv, gs)
+    # numpy restatement: fp32 subtract, fp32 divide, truncate toward zero
+    n = B * N * D * H * W
+    rel = ((coor.reshape(-1, 3) - lo) / iv).astype(np.float32)
+    cell = np.trunc(rel).astype(np.int64)
+    batch = np.repeat(np.arange(B), n // B)
+    kept = np.all((cell >= 0) & (cell < gs.astype(np.int64)), axis=1)
+    ranks_depth = np.arange(n, dtype=np.int64)
+    ranks_feat = (np.arange(n // D).reshape(B, N, 1, H, W) +
+                  np.zeros((1, 1, D, 1, 1), np.int64)).reshape(-1)
+    X, Y, Z = (int(v) for v in gs)
+    rank = (batch * (Z * Y * X) + cell[:, 2] * (Y * X) + cell[:, 1] * X +
+            cell[:, 0])
+    rank, rd, rf = rank[kept], ranks_depth[kept], ranks_feat[kept]
+    order = np.argsort(rank, kind="stable")
+    rank, rd, rf = rank[order], rd[order], rf[order]
+    if len(rank) == 0:
+        assert all(o is None for o in got)
+        return
+    starts = np.flatnonzero(np.r_[True, rank[1:] != rank[:-1]])
+    lengths = np.diff(np.r_[starts, len(rank)])
+    rb, grd, grf, st, ln = got
+    np.testing.assert_array_equal(rb, rank.astype(np.int32))
+    np.testing.assert_array_equal(st, starts.astype(np.int32))
+    np.testing.assert_array_equal(ln, lengths.astype(np.int32))
+    np.testing.assert_array_equal(grd, rd.astype(np.int32))   # stable order
+    np.testing.assert_array_equal(grf, rf.astype(np.int32))
