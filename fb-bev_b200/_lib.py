@@ -45,10 +45,10 @@ _SIGNATURES = {
     "fbbev_voxel_prepare": (
         ctypes.c_int, [_p] + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
     "fbbev_voxel_prepare_cams": (
-        ctypes.c_int, [_p] * 8 + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+        ctypes.c_int, [_p] * 8 + [_i32] * 6 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
     "fbbev_point_sampling": (
-        ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32, _i32] +
-        [ctypes.c_float] * 3 + [_p] * 4),
+        ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32] * 3 +
+        [ctypes.c_float] * 4 + [_p] * 4),
     "fbbev_msda_fwd": (ctypes.c_int, [_p] * 5 + [_i32] * 7 + [_p, _p]),
     "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
     "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p, _p]),
@@ -63,6 +63,7 @@ _SIGNATURES = {
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -96,7 +97,7 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.fbbev_abi_version() != 1:
+        if _lib.fbbev_abi_version() != ABI_VERSION:
             raise FbbevError("libfbbev_b200.so ABI version mismatch")
     return _lib
 
@@ -132,6 +133,24 @@ def require_cuda(*tensors):
         elif t.device != dev:
             raise FbbevError("all tensors must be on the same CUDA device")
     return dev
+
+
+def matmul_order_flags(*mats):
+    """FBBEV_ORDER_SEQ_* bits for the 3x3 matrix stacks a geometry kernel
+    applies per point, one bit per argument.
+
+    torch's broadcast ``M.view(.., 1, 1, 1, 3, 3).matmul(pts)`` rounds each
+    output as ``fma(m1, x1, m0*x0) + m2*x2`` on B200 -- except when M is ONE
+    matrix in the column-major layout ``torch.inverse`` returns: the expand is
+    then a stride-0 view, cuBLAS receives op 't' and its kernel for that case
+    uses the sequential FMA chain (tools/micro/matmul_order2.py).  The flags
+    are derived from the tensors exactly as the eager chain would see them, so
+    they must be taken BEFORE any ``.contiguous()``."""
+    flags = 0
+    for i, m in enumerate(mats):
+        if m.numel() == 9 and m.stride(-1) != 1:
+            flags |= 1 << i
+    return flags
 
 
 def c_floats(vals):

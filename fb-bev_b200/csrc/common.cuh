@@ -34,4 +34,28 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 
+// y = M x for a row-major 3x3 M, in the rounding order torch's broadcast
+// (..,3,3) @ (..,3,1) matmul has on B200 (torch 2.11 / cuBLAS 12.8; identified
+// by tools/micro/matmul_order2.py over all 18 FMA / non-FMA association orders,
+// 100 % of 5.4 M points at five problem sizes):
+//   y_i = fma(m_i1, x_1, m_i0 * x_0) + m_i2 * x_2            (batched 'n' kernel)
+// and, when `seq` is set, the sequential FMA chain
+//   y_i = fma(m_i2, x_2, fma(m_i1, x_1, m_i0 * x_0))
+// which cuBLAS uses for a single column-major matrix broadcast over the batch
+// (torch.inverse returns column-major; with one matrix in total the expand is a
+// stride-0 view and the transposed layout reaches cuBLAS as op 't').
+__device__ __forceinline__ float dot3_ref(float m0, float m1, float m2, float x,
+                                          float y, float z, bool seq) {
+  const float s = __fmaf_rn(m1, y, __fmul_rn(m0, x));
+  return seq ? __fmaf_rn(m2, z, s) : __fadd_rn(s, __fmul_rn(m2, z));
+}
+__device__ __forceinline__ void mat3_apply_ref(const float* __restrict__ m,
+                                               float x, float y, float z,
+                                               bool seq, float& ox, float& oy,
+                                               float& oz) {
+  ox = dot3_ref(__ldg(m + 0), __ldg(m + 1), __ldg(m + 2), x, y, z, seq);
+  oy = dot3_ref(__ldg(m + 3), __ldg(m + 4), __ldg(m + 5), x, y, z, seq);
+  oz = dot3_ref(__ldg(m + 6), __ldg(m + 7), __ldg(m + 8), x, y, z, seq);
+}
+
 }  // namespace fbbev

@@ -9,25 +9,21 @@
 //   p = inv(bda) ref;  p -= trans;  c = inv(rots inv(K)) p;
 //   (u, v) = c.xy / max(c.z, eps);  (u, v, d) = post_rots (u, v, c.z) + post_trans;
 //   u /= W_in;  v /= H_in;  mask = d > eps and eps < u, v < 1 - eps
-// in fp32 with one FMA per term; it agrees with the cuBLAS evaluation to fp32
-// rounding (the library's internal summation order is not specified).
+// in fp32, every 3x3 product in the rounding order torch's broadcast matmul has
+// on this device (mat3_apply_ref, common.cuh) and the two normalisations as the
+// multiplications by a reciprocal that torch's CUDA `tensor /= python_scalar`
+// performs (BinaryDivTrueKernel.cu), so ref_cam / depth / mask are bit-identical
+// to the eager chain's (tests/test_backward_gpu.py::test_fused_point_sampling_bit_exact).
 #include "common.cuh"
 
 namespace fbbev {
-
-__device__ __forceinline__ void mat3v(const float* __restrict__ m, float x,
-                                      float y, float z, float& ox, float& oy,
-                                      float& oz) {
-  ox = fmaf(__ldg(m + 2), z, fmaf(__ldg(m + 1), y, __ldg(m + 0) * x));
-  oy = fmaf(__ldg(m + 5), z, fmaf(__ldg(m + 4), y, __ldg(m + 3) * x));
-  oz = fmaf(__ldg(m + 8), z, fmaf(__ldg(m + 7), y, __ldg(m + 6) * x));
-}
 
 struct SamplingParams {
   const float *X, *Y, *Z;          // voxel-centre coordinates per axis
   const float *inv_bda, *trans, *ego2cam, *post_rots, *post_trans;
   int nX, nY, nZ, B, N;
-  float inv_unused, w_in, h_in, eps, one_minus_eps;
+  int order;                       // FBBEV_ORDER_SEQ_* bits
+  float inv_w, inv_h, eps, one_minus_eps;
 };
 
 __global__ void __launch_bounds__(256) point_sampling_kernel(
@@ -48,24 +44,25 @@ __global__ void __launch_bounds__(256) point_sampling_kernel(
   const int bn = b * P.N + n;
 
   float x, y, zz;
-  mat3v(P.inv_bda + b * 9, __ldg(P.X + ix), __ldg(P.Y + iy), __ldg(P.Z + z), x,
-        y, zz);
+  mat3_apply_ref(P.inv_bda + b * 9, __ldg(P.X + ix), __ldg(P.Y + iy),
+                 __ldg(P.Z + z), (P.order & 1) != 0, x, y, zz);
   const float* tr = P.trans + bn * 3;
   x = __fsub_rn(x, __ldg(tr + 0));
   y = __fsub_rn(y, __ldg(tr + 1));
   zz = __fsub_rn(zz, __ldg(tr + 2));
   float cx, cy, cz;
-  mat3v(P.ego2cam + bn * 9, x, y, zz, cx, cy, cz);
+  mat3_apply_ref(P.ego2cam + bn * 9, x, y, zz, (P.order & 2) != 0, cx, cy, cz);
   const float den = fmaxf(cz, P.eps);
   const float u = __fdiv_rn(cx, den), v = __fdiv_rn(cy, den);
   float pu, pv, pd;
-  mat3v(P.post_rots + bn * 9, u, v, cz, pu, pv, pd);
+  mat3_apply_ref(P.post_rots + bn * 9, u, v, cz, (P.order & 4) != 0, pu, pv,
+                 pd);
   const float* pt = P.post_trans + bn * 3;
   pu = __fadd_rn(pu, __ldg(pt + 0));
   pv = __fadd_rn(pv, __ldg(pt + 1));
   pd = __fadd_rn(pd, __ldg(pt + 2));
-  pu = __fdiv_rn(pu, P.w_in);
-  pv = __fdiv_rn(pv, P.h_in);
+  pu = __fmul_rn(pu, P.inv_w);  // cam[..., 0] /= ogfW  on CUDA: a * (1 / b)
+  pv = __fmul_rn(pv, P.inv_h);
   const bool m = pd > P.eps && pu > P.eps && pu < P.one_minus_eps &&
                  pv > P.eps && pv < P.one_minus_eps;
   reinterpret_cast<float2*>(ref_cam)[i] = make_float2(pu, pv);
@@ -80,9 +77,10 @@ using namespace fbbev;
 FBBEV_API int fbbev_point_sampling(
     const float* X, const float* Y, const float* Z, int32_t nX, int32_t nY,
     int32_t nZ, const float* inv_bda, const float* trans, const float* ego2cam,
-    const float* post_rots, const float* post_trans, int32_t B, int32_t N,
-    float w_in, float h_in, float eps, float* ref_cam, float* depth,
-    uint8_t* mask, fbbev_stream_t stream) {
+    const float* post_rots, const float* post_trans, int32_t order_flags,
+    int32_t B, int32_t N, float w_in, float h_in, float eps,
+    float one_minus_eps, float* ref_cam, float* depth, uint8_t* mask,
+    fbbev_stream_t stream) {
   if (nX <= 0 || nY <= 0 || nZ <= 0 || B <= 0 || N <= 0)
     return FBBEV_ERR_INVALID_ARGUMENT;
   if (!X || !Y || !Z || !inv_bda || !trans || !ego2cam || !post_rots ||
@@ -93,8 +91,11 @@ FBBEV_API int fbbev_point_sampling(
   P.inv_bda = inv_bda; P.trans = trans; P.ego2cam = ego2cam;
   P.post_rots = post_rots; P.post_trans = post_trans;
   P.nX = nX; P.nY = nY; P.nZ = nZ; P.B = B; P.N = N;
-  P.inv_unused = 0.f; P.w_in = w_in; P.h_in = h_in; P.eps = eps;
-  P.one_minus_eps = (float)(1.0 - (double)eps);
+  P.order = order_flags;
+  P.inv_w = 1.0f / w_in;  // accscalar_t(1.0) / b, rounded once to fp32
+  P.inv_h = 1.0f / h_in;
+  P.eps = eps;
+  P.one_minus_eps = one_minus_eps;
   const int64_t total = (int64_t)N * B * nY * nX * nZ;
   count_launch();
   point_sampling_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0,

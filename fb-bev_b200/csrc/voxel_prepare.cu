@@ -76,9 +76,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_voxelize_kernel(
 // the voxelisation.  The chain is the reference's --
 //   p = frustum - post_trans;  p = inv(post_rots) p;  p = (p.x p.z, p.y p.z, p.z);
 //   p = (rots inv(K)) p + trans;  p = bda p
-// -- in fp32 with one FMA per term.  torch evaluates the same chain through
-// cuBLAS batched products whose internal rounding is library- and
-// device-dependent, so the two agree to fp32 rounding, not bit for bit.
+// -- in fp32, every 3x3 product in the rounding order torch's broadcast matmul
+// has on this device (mat3_apply_ref, common.cuh), so the coordinate -- and the
+// voxel it truncates into -- is bit-identical to the eager chain's
+// (tests/test_forward_gpu.py::test_fused_geometry_bit_exact).
 struct CamGeom {
   const float* us;      // [W]  frustum u (linspace over the input width)
   const float* vs;      // [H]  frustum v
@@ -89,15 +90,8 @@ struct CamGeom {
   const float* trn;     // [B*N][3] trans
   const float* bda;     // [B][9]
   int N, D, H, W;
+  int order;            // FBBEV_ORDER_SEQ_* bits (see include/fbbev_b200.h)
 };
-
-__device__ __forceinline__ void mat3_apply(const float* __restrict__ m, float x,
-                                           float y, float z, float& ox,
-                                           float& oy, float& oz) {
-  ox = fmaf(m[2], z, fmaf(m[1], y, m[0] * x));
-  oy = fmaf(m[5], z, fmaf(m[4], y, m[3] * x));
-  oz = fmaf(m[8], z, fmaf(m[7], y, m[6] * x));
-}
 
 __global__ void __launch_bounds__(kPrepThreads) prep_voxelize_cams_kernel(
     CamGeom cg, int64_t n_pts, int64_t per_b, GridParams g,
@@ -116,16 +110,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_voxelize_cams_kernel(
   float y = __fsub_rn(__ldg(cg.vs + h), __ldg(pt + 1));
   float z = __fsub_rn(__ldg(cg.ds + d), __ldg(pt + 2));
   float a, bb, c;
-  mat3_apply(cg.ipr + bn * 9, x, y, z, a, bb, c);
+  mat3_apply_ref(cg.ipr + bn * 9, x, y, z, (cg.order & 1) != 0, a, bb, c);
   x = __fmul_rn(a, c);
   y = __fmul_rn(bb, c);
   z = c;
-  mat3_apply(cg.comb + bn * 9, x, y, z, a, bb, c);
+  mat3_apply_ref(cg.comb + bn * 9, x, y, z, (cg.order & 2) != 0, a, bb, c);
   const float* tr = cg.trn + bn * 3;
   a = __fadd_rn(a, __ldg(tr + 0));
   bb = __fadd_rn(bb, __ldg(tr + 1));
   c = __fadd_rn(c, __ldg(tr + 2));
-  mat3_apply(cg.bda + b * 9, a, bb, c, x, y, z);
+  mat3_apply_ref(cg.bda + b * 9, a, bb, c, (cg.order & 4) != 0, x, y, z);
   voxelize_point(x, y, z, p, per_b, g, rank, hist);
 }
 
@@ -397,8 +391,9 @@ FBBEV_API int fbbev_voxel_prepare(
 FBBEV_API int fbbev_voxel_prepare_cams(
     const float* frustum_u, const float* frustum_v, const float* frustum_d,
     const float* inv_post_rots, const float* post_trans, const float* cam2ego,
-    const float* trans, const float* bda, int32_t B, int32_t N, int32_t D,
-    int32_t H, int32_t W, const float* lo_host, const float* iv_host,
+    const float* trans, const float* bda, int32_t order_flags, int32_t B,
+    int32_t N, int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host,
     const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
     int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
     int32_t* counts, void* workspace, size_t workspace_bytes,
@@ -411,6 +406,7 @@ FBBEV_API int fbbev_voxel_prepare_cams(
   cg.ipr = inv_post_rots; cg.ptr = post_trans; cg.comb = cam2ego;
   cg.trn = trans; cg.bda = bda;
   cg.N = N; cg.D = D; cg.H = H; cg.W = W;
+  cg.order = order_flags;
   return voxel_prepare_impl(nullptr, &cg, B, N, D, H, W, lo_host, iv_host,
                             gs_host, ranks_bev, ranks_depth, ranks_feat,
                             interval_starts, interval_lengths, counts,

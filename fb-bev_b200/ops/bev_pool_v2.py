@@ -288,11 +288,13 @@ def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
 
     frustum_axes = (u [W], v [H], d [D]) CUDA float tensors;
     inv_post_rots / cam2ego (B,N,3,3); post_trans / trans (B,N,3); bda (B,3,3).
-    Returns a :class:`VoxelIndex`.  Agrees with the two-step route to fp32
-    rounding of the coordinates (see include/fbbev_b200.h)."""
+    Returns a :class:`VoxelIndex`, bit-identical to the two-step route: the
+    kernel rounds every 3x3 product as torch's broadcast matmul does on this
+    device (see include/fbbev_b200.h, ``_lib.matmul_order_flags``)."""
     fu, fv, fd = (t.contiguous().float() for t in frustum_axes)
     dev = _lib.require_cuda(fu, fv, fd, inv_post_rots, post_trans, cam2ego,
                             trans, bda)
+    order = _lib.matmul_order_flags(inv_post_rots, cam2ego, bda)
     mats = [t.contiguous().float() for t in
             (inv_post_rots, post_trans, cam2ego, trans, bda)]
     B, N = mats[0].shape[:2]
@@ -312,7 +314,7 @@ def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
         rc = L.fbbev_voxel_prepare_cams(
             _lib.ptr(fu), _lib.ptr(fv), _lib.ptr(fd), _lib.ptr(mats[0]),
             _lib.ptr(mats[1]), _lib.ptr(mats[2]), _lib.ptr(mats[3]),
-            _lib.ptr(mats[4]), B, N, D, H, W, _lib.c_floats(lo),
+            _lib.ptr(mats[4]), order, B, N, D, H, W, _lib.c_floats(lo),
             _lib.c_floats(iv), _lib.c_floats(gs), _lib.ptr(idx[0]),
             _lib.ptr(idx[1]), _lib.ptr(idx[2]), _lib.ptr(idx[3]),
             _lib.ptr(idx[4]), _lib.ptr(counts), _lib.ptr(ws), ws_bytes,

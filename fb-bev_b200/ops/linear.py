@@ -41,6 +41,25 @@ def _pack(weight):
     return blocks
 
 
+def invalidate(obj):
+    """Drop the packed-weight images cached for ``obj`` (an nn.Module, walked
+    recursively, or a single weight tensor).
+
+    The caches key on ``Tensor._version``, which in-place updates through
+    ``param.data`` (EMA hooks, some checkpoint loaders) do NOT bump -- call
+    this after such an update.  ``optimizer.step()``, ``load_state_dict`` and
+    ordinary in-place ops on the parameter are detected automatically."""
+    if isinstance(obj, torch.Tensor):
+        if hasattr(obj, "_fbbev_packed"):
+            del obj._fbbev_packed
+        return
+    for m in obj.modules():
+        m.__dict__.pop("_pair_cache", None)
+        for p in m.parameters(recurse=False):
+            if hasattr(p, "_fbbev_packed"):
+                del p._fbbev_packed
+
+
 def ln_supported(n):
     """The LayerNorm epilogue keeps whole rows in shared memory beside two
     pipeline stages (linear_tf32.cu): n <= 80 with the 40-float K-block."""

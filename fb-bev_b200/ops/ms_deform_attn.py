@@ -19,8 +19,18 @@ from .. import _lib
 
 __all__ = ['MultiScaleDeformableAttnFunction_fp32',
            'MultiScaleDeformableAttnFunction_fp16', 'ms_deform_attn_forward',
-           'ms_deform_attn_fused', 'da_spatial_cross_attention_core',
-           'point_sampling']
+           'ms_deform_attn_fused', 'ms_deform_attn_unfused',
+           'da_spatial_cross_attention_core',
+           'da_spatial_cross_attention_core_autograd', 'point_sampling',
+           'needs_grad']
+
+
+def needs_grad(*tensors):
+    """True when autograd is recording and one of ``tensors`` takes part in it:
+    the forward-only fused kernels must not be used then (their outputs carry
+    no grad_fn and would silently cut the graph)."""
+    return torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in tensors)
 
 
 def _i64(t, dev):
@@ -123,6 +133,70 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index,
     return out
 
 
+def ms_deform_attn_unfused(value, spatial_shapes, level_start_index,
+                           reference_points, sampling_offsets,
+                           attention_logits, im2col_step=64):
+    """Differentiable twin of :func:`ms_deform_attn_fused`: softmax and the
+    sampling locations in PyTorch (as mmcv's module does), the sampling through
+    ``MultiScaleDeformableAttnFunction_fp32`` (forward ``fbbev_msda_fwd``,
+    backward ``fbbev_msda_bwd``).  Same arguments and result."""
+    lg = attention_logits
+    w = lg.flatten(3).softmax(-1).view_as(lg)
+    wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+    loc = reference_points[:, :, None, :, None, :] + \
+        sampling_offsets / wh[None, None, None, :, None, :]
+    return MultiScaleDeformableAttnFunction_fp32.apply(
+        value, spatial_shapes, level_start_index, loc, w, im2col_step)
+
+
+def da_spatial_cross_attention_core_autograd(
+        value, depth_prob, reference_points_cam, bev_query_depth, per_cam_mask,
+        sampling_offsets, attention_logits, spatial_shapes, level_start_index,
+        dbound, num_Z_anchors, im2col_step=64):
+    """Differentiable twin of :func:`da_spatial_cross_attention_core` (same
+    arguments and result) for training: every (camera, query) pair is evaluated
+    densely and the pairs a camera does not see are masked out of the mean, so
+    there is no ``nonzero()`` host synchronisation and gradients reach
+    ``value`` (-> value_proj, image features), the offsets / logits (-> their
+    Linears, the BEV queries) and ``depth_prob`` (-> the depth net), as through
+    the reference's ``MultiScaleDeformableAttnFunction`` calls
+    (spatial_cross_attention_depth.py:584-595)."""
+    apply = MultiScaleDeformableAttnFunction_fp32.apply
+    N, bs, nq, Z, _ = reference_points_cam.shape
+    _, _, heads, L, P, _ = sampling_offsets.shape
+    DC = depth_prob.shape[-1]
+    E = value.shape[2] * value.shape[3]
+    assert Z == num_Z_anchors and P % Z == 0
+    w = attention_logits.flatten(3).softmax(-1).view_as(attention_logits)
+    wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]],
+                     -1).to(sampling_offsets.dtype)
+    off = sampling_offsets / wh[None, None, None, :, None, :]
+    ref = reference_points_cam.permute(1, 0, 2, 3, 4)       # (bs, N, nq, Z, 2)
+    # point index = p * Z + z   (:563-570)
+    loc = ref[:, :, :, None, None, None, :, :] + off.view(
+        bs, 1, nq, heads, L, P // Z, Z, 2)
+    loc = loc.reshape(bs * N, nq, heads, L, P, 2)
+    d = bev_query_depth
+    if d.dim() == 5:
+        d = d[..., 0]
+    bins = torch.floor((d.permute(1, 0, 2, 3) - dbound[0]) / dbound[2])
+    bins = bins.clamp(0, DC - 1).long().reshape(bs * N, nq, Z, 1)
+    depth_ref = ref.reshape(bs * N, nq * Z, 1, 1, 1, 2).contiguous()
+    dsamp = apply(depth_prob.unsqueeze(2).contiguous(), spatial_shapes[0:1],
+                  level_start_index[0:1], depth_ref,
+                  torch.ones_like(depth_ref[..., 0]), im2col_step)
+    dw = dsamp.view(bs * N, nq, Z, DC).gather(-1, bins).squeeze(-1)
+    dw = dw.unsqueeze(2).repeat(1, 1, P // Z, 1).reshape(bs * N, nq, P)
+    wts = w.unsqueeze(1).expand(bs, N, nq, heads, L, P).reshape(
+        bs * N, nq, heads, L, P) * dw[:, :, None, None, :]      # :592
+    out = apply(value, spatial_shapes, level_start_index, loc, wts,
+                im2col_step).view(bs, N, nq, E)
+    seen = per_cam_mask.bool().any(-1).permute(1, 0, 2)      # (bs, N, nq)
+    slots = (out * seen[..., None].to(out.dtype)).sum(1)
+    count = seen.sum(1).clamp(min=1).to(out.dtype)
+    return slots / count[..., None]
+
+
 def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
                                     bev_query_depth, per_cam_mask,
                                     sampling_offsets, attention_logits,
@@ -177,10 +251,12 @@ def point_sampling(axes, inv_bda, trans, ego2cam, post_rots, post_trans,
     axes = (X [nX], Y [nY], Z [nZ]) voxel-centre coordinates; inv_bda (B,3,3);
     ego2cam / post_rots (B,N,3,3); trans / post_trans (B,N,3);
     input_size = (H_in, W_in).  Returns ``(reference_points_cam (N,B,nq,Z,2),
-    mask (N,B,nq,Z) bool, depth (N,B,nq,Z,1))`` with nq = nY*nX."""
+    mask (N,B,nq,Z) bool, depth (N,B,nq,Z,1))`` with nq = nY*nX, bit-identical
+    to the eager chain on this device."""
     X, Y, Z = (t.contiguous().float() for t in axes)
     dev = _lib.require_cuda(X, Y, Z, inv_bda, trans, ego2cam, post_rots,
                             post_trans)
+    order = _lib.matmul_order_flags(inv_bda, ego2cam, post_rots)
     mats = [t.contiguous().float() for t in
             (inv_bda, trans, ego2cam, post_rots, post_trans)]
     B, N = mats[1].shape[:2]
@@ -193,8 +269,9 @@ def point_sampling(axes, inv_bda, trans, ego2cam, post_rots, post_trans,
         rc = _lib.lib().fbbev_point_sampling(
             _lib.ptr(X), _lib.ptr(Y), _lib.ptr(Z), nX, nY, nZ,
             _lib.ptr(mats[0]), _lib.ptr(mats[1]), _lib.ptr(mats[2]),
-            _lib.ptr(mats[3]), _lib.ptr(mats[4]), B, N, float(input_size[1]),
-            float(input_size[0]), float(eps), _lib.ptr(ref), _lib.ptr(dep),
-            _lib.ptr(msk), _lib.stream_ptr(dev))
+            _lib.ptr(mats[3]), _lib.ptr(mats[4]), order, B, N,
+            float(input_size[1]), float(input_size[0]), float(eps),
+            float(1.0 - eps), _lib.ptr(ref), _lib.ptr(dep), _lib.ptr(msk),
+            _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_point_sampling')
     return ref, msk.view(torch.bool), dep

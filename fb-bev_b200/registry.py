@@ -13,6 +13,7 @@ That registry + kwargs contract is the plugin API this package preserves:
   from the very same config dicts.
 """
 import copy
+import os
 
 import torch.nn as nn
 
@@ -104,16 +105,38 @@ def _upstream_registries():
 _UPSTREAM = _upstream_registries()
 
 
-def register(registry_name, name=None):
-    """Class decorator: register locally and, if present, upstream."""
+def register(registry_name, name=None, upstream=True):
+    """Class decorator: register locally and, if present, upstream.
+
+    ``upstream=False`` is for the replacements of GENERIC mmcv bricks
+    (``MultiScaleDeformableAttention``, ``FFN``): every other model in the
+    process resolves those names through mmcv's global registries, so they are
+    only overridden there on request (``FBBEV_OVERRIDE_MMCV=1`` or
+    :func:`override_upstream_generic`).  The plugin's own modules never need
+    it: they build their children through the local registries below."""
     def _deco(cls):
         _LOCAL[registry_name].register_module(name=name, force=True,
                                               module=cls)
+        if upstream or os.environ.get('FBBEV_OVERRIDE_MMCV', '0') == '1':
+            up = _UPSTREAM.get(registry_name)
+            if up is not None:  # pragma: no cover
+                up.register_module(name=name, force=True, module=cls)
+        else:
+            _GENERIC.append((registry_name, name, cls))
+        return cls
+    return _deco
+
+
+_GENERIC = []
+
+
+def override_upstream_generic():
+    """Opt in: also replace mmcv's global ``MultiScaleDeformableAttention`` and
+    ``FFN`` registrations with this package's classes."""
+    for registry_name, name, cls in _GENERIC:
         up = _UPSTREAM.get(registry_name)
         if up is not None:  # pragma: no cover
             up.register_module(name=name, force=True, module=cls)
-        return cls
-    return _deco
 
 
 def build_attention(cfg, **kw):

@@ -48,7 +48,9 @@ from .forward_projection import inv3x3_many
 from ..ops import ms_deform_attn as _msda_ops
 from ..ops.ms_deform_attn import (MultiScaleDeformableAttnFunction_fp32,
                                   da_spatial_cross_attention_core,
-                                  ms_deform_attn_fused)
+                                  da_spatial_cross_attention_core_autograd,
+                                  ms_deform_attn_fused, ms_deform_attn_unfused,
+                                  needs_grad)
 from ..registry import (BaseModule, build_attention,
                         build_feedforward_network, build_positional_encoding,
                         build_transformer, build_transformer_layer,
@@ -191,7 +193,7 @@ class CustormLearnedPositionalEncoding(BaseModule):
 # ---------------------------------------------------------------------------
 # mmcv.cnn.bricks.transformer.FFN  (state-dict keys layers.0.0.*, layers.1.*)
 # ---------------------------------------------------------------------------
-@register('FEEDFORWARD_NETWORK')
+@register('FEEDFORWARD_NETWORK', upstream=False)
 class FFN(BaseModule):
 
     def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
@@ -240,7 +242,7 @@ class FFN(BaseModule):
 # ---------------------------------------------------------------------------
 # mmcv.ops.MultiScaleDeformableAttention (encoder self-attention)
 # ---------------------------------------------------------------------------
-@register('ATTENTION')
+@register('ATTENTION', upstream=False)
 class MultiScaleDeformableAttention(BaseModule):
     """Deformable self-attention over the BEV map.  Same parameters and
     ``forward`` contract as mmcv's module; sampling runs in the fused kernel
@@ -316,8 +318,12 @@ class MultiScaleDeformableAttention(BaseModule):
         if reference_points.shape[-1] != 2:
             raise ValueError('Last dim of reference_points must be 2, but get '
                              f'{reference_points.shape[-1]} instead.')
-        output = ms_deform_attn_fused(value, spatial_shapes, level_start_index,
-                                      reference_points, offsets, logits)
+        # the fused sampling kernel is forward-only: with autograd recording,
+        # take the differentiable route (mmcv's own op sequence)
+        core = ms_deform_attn_unfused if needs_grad(value, offsets, logits) \
+            else ms_deform_attn_fused
+        output = core(value, spatial_shapes, level_start_index,
+                      reference_points, offsets, logits)
         if fused:
             res = identity if self.batch_first else identity.permute(1, 0, 2)
             output = _linear(self.output_proj, output, residual=res,
@@ -534,12 +540,16 @@ class DA_SpatialCrossAttention(BaseModule):
         depth_prob = pred_img_depth.reshape(B * N, DC, H * W).permute(0, 2, 1)
         num_cams, n_value, bs, E = value.shape
         value = value.permute(2, 0, 1, 3).reshape(bs * num_cams, n_value, E)
-        kpm = key_padding_mask
-        v = da.project_value(value.float(), kpm)
+        # key_padding_mask is NOT forwarded: the reference's call of the
+        # deformable attention omits it (spatial_cross_attention_depth.py:201-206)
+        v = da.project_value(value.float())
         offsets, logits = da.project_query(query)
         if bev_query_depth.dim() == 5:
             bev_query_depth = bev_query_depth[..., 0]
-        slots = da_spatial_cross_attention_core(
+        core = da_spatial_cross_attention_core
+        if needs_grad(v, depth_prob, offsets, logits):
+            core = da_spatial_cross_attention_core_autograd
+        slots = core(
             v, depth_prob, reference_points_cam, bev_query_depth,
             per_cam_mask_list, offsets, logits, spatial_shapes,
             level_start_index, self.dbound, da.num_Z_anchors)
@@ -592,7 +602,6 @@ class DA_SpatialCrossAttention(BaseModule):
             spatial_shapes=spatial_shapes, level_start_index=level_start_index,
             bev_query_depth=onehot.view(bs * num_cams, max_len, Z, DC),
             pred_img_depth=depth_prob.contiguous(),
-            key_padding_mask=key_padding_mask,
         ).view(bs, num_cams, max_len, E)
         slots = torch.zeros_like(query)
         for j in range(bs):
@@ -778,9 +787,13 @@ class bevformer_encoder(BaseModule):
     attribute to False turns it off): ``forward`` projects the reference points
     with one kernel (``fbbev_point_sampling``) instead of ``point_sampling``'s
     ~20 eager ops (8 ms of cuBLAS batched 3x3 products for 200x200x4 points x 6
-    cameras on B200).  Same fp32 chain, rounding order inside the 3x3 products
-    differs (cuBLAS does not specify its own).  ``point_sampling`` keeps the
-    reference's exact contract."""
+    cameras on B200).  Same fp32 chain in the same rounding order as the eager
+    ops have on this device (3x3 products as torch's broadcast matmul rounds
+    them, ``/= scalar`` as the multiplication by a reciprocal torch's CUDA
+    kernel performs): reference points, depths and masks are bit-identical to
+    ``point_sampling`` (tests/test_backward_gpu.py::
+    test_fused_point_sampling_bit_exact), which keeps the reference's exact
+    contract."""
 
     fused_geometry = os.environ.get('FBBEV_EXACT_GEOMETRY', '0') != '1'
 
@@ -912,13 +925,13 @@ class bevformer_encoder(BaseModule):
         output = bev_query
         intermediate = []
         cache = self.__dict__.setdefault('_ref2d_cache', {})
-        key = (bev_h, bev_w, bev_query.size(1), str(bev_query.device),
-               bev_query.dtype)
-        if key not in cache:  # constant for a given BEV size / batch / device
-            cache[key] = self.get_reference_points(
+        ck = (bev_h, bev_w, bev_query.size(1), str(bev_query.device),
+              bev_query.dtype)
+        if ck not in cache:  # constant for a given BEV size / batch / device
+            cache[ck] = self.get_reference_points(
                 bev_h, bev_w, dim='2d', bs=bev_query.size(1),
                 device=bev_query.device, dtype=bev_query.dtype)
-        ref_2d = cache[key]
+        ref_2d = cache[ck]
         if self.fused_geometry and bev_query.is_cuda:
             ref_3d = None  # only consumed by point_sampling
             reference_points_cam, per_cam_mask_list, bev_query_depth = \

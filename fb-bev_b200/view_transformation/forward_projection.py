@@ -15,9 +15,13 @@ What changed underneath:
 * ``accelerate=True`` caches the device index (the reference's 3-D class
   asserts out at view_transformer.py:628; the 2-D class supports it, :271-283).
 
-Geometry (``get_lidar_coor``) deliberately stays in PyTorch with the reference's
-operation order: the integer voxel path is only bit-exact if the fp32
-coordinates it starts from are rounded identically.
+Geometry: ``get_lidar_coor`` keeps the reference's operation sequence in
+PyTorch.  ``forward`` evaluates the same chain inside the voxelisation kernel
+(``fused_geometry``), rounding every 3x3 product exactly as torch's broadcast
+matmul does on B200, so the integer index is bit-identical to
+``voxel_pooling_prepare_v2(get_lidar_coor(...))`` -- the integer voxel path is
+only bit-exact if the fp32 coordinates it starts from are rounded identically
+(SURVEY.md section 7.3; tests/test_forward_gpu.py::test_fused_geometry_bit_exact).
 """
 import torch
 import torch.nn as nn
@@ -68,9 +72,11 @@ class _LSSBase(BaseModule):
     kernel instead of materialising ``get_lidar_coor``'s (B,N,D,H,W,3) tensor
     through eager PyTorch (1.0 ms of cuBLAS batched 3x3 products for 338k points
     on B200 -- 15x the pooling kernel).  Both routes implement the same fp32
-    chain; they differ only in the rounding order inside the 3x3 products, which
-    cuBLAS does not specify either.  ``get_lidar_coor`` and
-    ``voxel_pooling_prepare_v2(coor)`` keep the reference's exact contract.
+    chain with the same rounding order (``mat3_apply_ref`` in csrc/common.cuh
+    reproduces the order of torch's broadcast matmul on this device, found with
+    tools/micro/matmul_order2.py), so the resulting index is identical, point
+    for point.  ``get_lidar_coor`` and ``voxel_pooling_prepare_v2(coor)`` keep
+    the reference's exact contract.
     """
 
     fused_geometry = os.environ.get('FBBEV_EXACT_GEOMETRY', '0') != '1'

@@ -31,7 +31,7 @@ extern "C" {
 #define FBBEV_ERR_WORKSPACE_TOO_SMALL (-2)
 #define FBBEV_ERR_UNSUPPORTED (-3)
 
-#define FBBEV_ABI_VERSION 1
+#define FBBEV_ABI_VERSION 2
 
 typedef void* fbbev_stream_t; /* cudaStream_t */
 
@@ -181,21 +181,26 @@ int fbbev_voxel_prepare(const float* coor, int32_t B, int32_t N, int32_t D,
  *   inv_post_rots = inverse(post_rots) (B*N,3,3); cam2ego = rots @ inverse(K)
  *   (B*N,3,3) -- the two tiny products the reference also forms before touching
  *   the points (:483-491); post_trans, trans (B*N,3); bda (B,3,3).
- * The per-point chain is evaluated in fp32 with one FMA per term; the reference
- * evaluates it through cuBLAS batched products with unspecified rounding order,
- * so a point within one fp32 ulp of a voxel face may be binned in the
- * neighbouring voxel.  fbbev_voxel_prepare on get_lidar_coor's own output is
- * the bit-exact route.
+ * The per-point chain is evaluated in fp32 in the rounding order the reference's
+ * eager chain has on this device (torch broadcast matmul -> cuBLAS): per output
+ * row fma(m1, x1, m0*x0) + m2*x2, or -- FBBEV_ORDER_SEQ_* bit set -- the
+ * sequential chain fma(m2, x2, fma(m1, x1, m0*x0)) cuBLAS uses when ONE
+ * column-major matrix (the layout torch.inverse returns) is broadcast over the
+ * whole batch.  order_flags: bit 0 inv_post_rots, bit 1 cam2ego, bit 2 bda.
+ * The index is bit-identical to fbbev_voxel_prepare on get_lidar_coor's output.
  */
+#define FBBEV_ORDER_SEQ_A 1
+#define FBBEV_ORDER_SEQ_B 2
+#define FBBEV_ORDER_SEQ_C 4
 int fbbev_voxel_prepare_cams(
     const float* frustum_u, const float* frustum_v, const float* frustum_d,
     const float* inv_post_rots, const float* post_trans, const float* cam2ego,
-    const float* trans, const float* bda, int32_t B, int32_t N, int32_t D,
-    int32_t H, int32_t W, const float* lo_host, const float* iv_host,
-    const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
-    int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
-    int32_t* counts, void* workspace, size_t workspace_bytes,
-    fbbev_stream_t stream);
+    const float* trans, const float* bda, int32_t order_flags, int32_t B,
+    int32_t N, int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host, const float* gs_host, int32_t* ranks_bev,
+    int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int32_t* counts, void* workspace,
+    size_t workspace_bytes, fbbev_stream_t stream);
 
 /* =====================================================================
  * B -- BEV -> image depth-aware spatial cross-attention (MSDeformAttn)
@@ -207,16 +212,21 @@ int fbbev_voxel_prepare_cams(
  * X [nX], Y [nY], Z [nZ]: voxel-centre coordinates per axis (get_reference_points
  * '3d', :64-70); inv_bda = inverse(bda) (B,3,3); ego2cam = inverse(rots @
  * inverse(K)) (B*N,3,3); trans, post_trans (B*N,3); post_rots (B*N,3,3);
- * (w_in, h_in) = data_config input_size; eps = 1e-5.
+ * (w_in, h_in) = data_config input_size; eps = 1e-5 and one_minus_eps =
+ * (float)(1.0 - 1e-5), the two scalars of the visibility test (:113-117).
+ * order_flags as for fbbev_voxel_prepare_cams: bit 0 inv_bda, bit 1 ego2cam,
+ * bit 2 post_rots.  The image-plane normalisation multiplies by (1 / w_in),
+ * (1 / h_in) as torch's CUDA `tensor /= python_scalar` does.
  * Outputs in the reference's layouts: ref_cam (N,B,nY*nX,nZ,2), depth
- * (N,B,nY*nX,nZ), mask (N,B,nY*nX,nZ) uint8.
+ * (N,B,nY*nX,nZ), mask (N,B,nY*nX,nZ) uint8; bit-identical to the eager chain.
  */
 int fbbev_point_sampling(
     const float* X, const float* Y, const float* Z, int32_t nX, int32_t nY,
     int32_t nZ, const float* inv_bda, const float* trans, const float* ego2cam,
-    const float* post_rots, const float* post_trans, int32_t B, int32_t N,
-    float w_in, float h_in, float eps, float* ref_cam, float* depth,
-    uint8_t* mask, fbbev_stream_t stream);
+    const float* post_rots, const float* post_trans, int32_t order_flags,
+    int32_t B, int32_t N, float w_in, float h_in, float eps,
+    float one_minus_eps, float* ref_cam, float* depth, uint8_t* mask,
+    fbbev_stream_t stream);
 
 /*
  * Drop-in for `ext_module.ms_deform_attn_forward` (mmcv-full 1.5.2 `_ext`)

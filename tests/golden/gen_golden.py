@@ -112,10 +112,59 @@ def gen_forward(ref):
              coor_override=lambda c: c * 0 + 100.0)
 
 
+def gen_forward_2d(ref):
+    """LSSViewTransformerFunction (view_transformer.py:24-311): the 2-D,
+    Z-collapsed variant, with and without the cached index
+    (``accelerate=True``, :266-283)."""
+    VT = ref.view_transformer.LSSViewTransformerFunction
+
+    def run_case(name, grid_config, input_size, downsample, B, N, C, seed):
+        cam = synthetic.make_cam_params(B, N, input_size=input_size,
+                                        jitter=1.0, seed=seed)
+        H, W = input_size[0] // downsample, input_size[1] // downsample
+        out = {}
+        for acc in (False, True):
+            vt = VT(grid_config=grid_config, input_size=input_size,
+                    downsample=downsample, accelerate=acc)
+            depth, feat = synthetic.make_depth_feat(B, N, vt.D, H, W, C,
+                                                    seed=seed)
+            out[acc] = vt(cam, feat, depth)
+            if acc:     # second call reuses the cached index (initial_flag)
+                depth2, feat2 = synthetic.make_depth_feat(B, N, vt.D, H, W, C,
+                                                          seed=seed + 50)
+                out['second'] = vt(cam, feat2, depth2)
+        save(name,
+             grid_x=np.array(grid_config['x'], np.float64),
+             grid_y=np.array(grid_config['y'], np.float64),
+             grid_z=np.array(grid_config['z'], np.float64),
+             grid_depth=np.array(grid_config['depth'], np.float64),
+             input_size=np.array(input_size), downsample=np.array(downsample),
+             rots=_np(cam[0]), trans=_np(cam[1]), intrins=_np(cam[2]),
+             post_rots=_np(cam[3]), post_trans=_np(cam[4]), bda=_np(cam[5]),
+             depth=_np(depth), feat=_np(feat), depth2=_np(depth2),
+             feat2=_np(feat2), bev=_np(out[False]), bev_acc=_np(out[True]),
+             bev_acc_second=_np(out['second']))
+
+    # BEVDet-style single-Z grid (accelerate squeezes Z, :283)
+    run_case('f2d_z1_6cam',
+             dict(x=[-40, 40, 4.0], y=[-40, 40, 4.0], z=[-5, 3, 8],
+                  depth=[2.0, 42.0, 4.0]), (64, 176), 16, B=2, N=6, C=8,
+             seed=13)
+    # several Z slices: Z collapsed into channels (:191)
+    run_case('f2d_z4_6cam',
+             dict(x=[-40, 40, 4.0], y=[-40, 40, 4.0], z=[-1, 5.4, 1.6],
+                  depth=[2.0, 42.0, 4.0]), (64, 176), 16, B=1, N=6, C=8,
+             seed=14)
+
+
 def main():
     ref = ref_import.load_reference()
     torch.manual_seed(0)
+    if os.environ.get("GOLDEN_ONLY", "") == "f2d":
+        gen_forward_2d(ref)
+        return
     gen_forward(ref)
+    gen_forward_2d(ref)
     try:
         import gen_golden_backward
         gen_golden_backward.gen_backward(ref, save)
