@@ -86,6 +86,8 @@ def build(verbose=False):
 def lib():
     """Load the library (never builds implicitly; never falls back)."""
     global _lib
+    if _proxy is not None and _lib is not None:
+        return _proxy
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise FbbevError(
@@ -100,6 +102,51 @@ def lib():
         if _lib.fbbev_abi_version() != ABI_VERSION:
             raise FbbevError("libfbbev_b200.so ABI version mismatch")
     return _lib
+
+
+class KernelTimer:
+    """Diagnostics: bracket every C-ABI launch with CUDA events on the calling
+    stream (``with KernelTimer() as t: ...; t.records``).  bench.py uses it to
+    report per-kernel times / roofline fractions measured live in the run; it
+    is off (zero overhead: ``lib()`` returns the CDLL itself) otherwise."""
+
+    _SKIP = ("fbbev_abi_version", "fbbev_debug_launch_count",
+             "fbbev_error_string", "fbbev_linear_packed_bytes",
+             "fbbev_bev_pool_v2_dense_workspace_bytes",
+             "fbbev_voxel_prepare_workspace_bytes")
+
+    def __init__(self):
+        self.records = []   # (name, args, start_event, end_event)
+        self._real = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if name in self._SKIP or not name.startswith("fbbev_"):
+            return fn
+
+        def timed(*args):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.records.append((name, args, e0, e1))
+            return rc
+        return timed
+
+    def __enter__(self):
+        global _proxy
+        self._real = lib()
+        _proxy = self
+        return self
+
+    def __exit__(self, *exc):
+        global _proxy
+        _proxy = None
+        return False
+
+
+_proxy = None
 
 
 def check(code, what):

@@ -16,7 +16,7 @@ BEV on every rank: one ``all_gather_into_tensor`` of the refined 2-D BEV
 import torch
 import torch.distributed as dist
 
-__all__ = ['frame_slice', 'shard_frames', 'gather_bev']
+__all__ = ['frame_slice', 'shard_frames', 'gather_bev', 'GatherBuffer']
 
 
 def frame_slice(n_frames, rank, world_size):
@@ -52,3 +52,30 @@ def gather_bev(local_bev, group=None):
                               tuple(local_bev.shape[1:]))
     dist.all_gather_into_tensor(out, local_bev, group=group)
     return out
+
+
+class GatherBuffer:
+    """Registered all-gather buffer for the refined BEV of every frame.
+
+    ``slot`` is this rank's (b_local, C, H, W) view inside the gathered
+    (b_total, C, H, W) tensor: pass it as ``BackwardProjection.forward(...,
+    out=buf.slot)`` so the module's final layout pass writes straight into the
+    exchange buffer, then ``buf.gather()`` runs the in-place
+    ``all_gather_into_tensor`` (NCCL in-place semantics: input = the rank's own
+    chunk of the output; SURVEY.md section 8e "fusion with the collective" --
+    a zero-copy hand-off, no staging copy on either side)."""
+
+    def __init__(self, b_local, C, H, W, device, dtype=torch.float32,
+                 group=None):
+        self.group = group
+        init = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if init else 1
+        self.rank = dist.get_rank(group) if init else 0
+        self.full = torch.empty((self.world * b_local, C, H, W), dtype=dtype,
+                                device=device)
+        self.slot = self.full[self.rank * b_local:(self.rank + 1) * b_local]
+
+    def gather(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.full, self.slot, group=self.group)
+        return self.full

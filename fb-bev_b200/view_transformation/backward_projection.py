@@ -96,11 +96,18 @@ def _linear(mod, x, relu=False, residual=None, norm=None):
     """``norm(act(mod(x)) + residual)`` in one kernel launch per <= 160 output
     columns (``mod`` an nn.Linear, ``norm`` an nn.LayerNorm or None)."""
     n, k = mod.weight.shape
-    if k % 4 or n % 4 or (norm is not None and not _linear_ops.ln_supported(n)):
+    if k % 4 or n % 4:
         y = mod(x)
         y = F.relu(y) if relu else y
         y = y + residual if residual is not None else y
         return norm(y) if norm is not None else y
+    if norm is not None and not _linear_ops.ln_supported(n):
+        # rows wider than the LayerNorm epilogue keeps in shared memory
+        # (n > 80, e.g. embed_dims 256): GEMM + bias + ReLU + residual stay in
+        # the tcgen05 kernel, the normalisation is a separate pass
+        y = _linear_ops.linear_fused(x, mod.weight, mod.bias, relu=relu,
+                                     residual=residual)
+        return norm(y)
     return _linear_ops.linear_fused(
         x, mod.weight, mod.bias, relu=relu, residual=residual,
         ln_weight=None if norm is None else norm.weight,
@@ -1059,9 +1066,13 @@ class BackwardProjection(BaseModule):
         self.transformer.init_weights()
 
     def forward(self, mlvl_feats, img_metas, lss_bev=None, gt_bboxes_3d=None,
-                cam_params=None, pred_img_depth=None, bev_mask=None):
+                cam_params=None, pred_img_depth=None, bev_mask=None, out=None):
         """mlvl_feats: list of (B, N, C, H, W); lss_bev (B, C, bev_h, bev_w);
-        pred_img_depth (B, N, DC, H, W).  Returns (B, C, bev_h, bev_w)."""
+        pred_img_depth (B, N, DC, H, W).  Returns (B, C, bev_h, bev_w).
+
+        ``out`` (optional, not in the reference): a contiguous (B, C, bev_h,
+        bev_w) tensor to write the result into -- e.g. this rank's slot of an
+        all-gather buffer (sharding.py), which saves the copy into it."""
         bs = mlvl_feats[0].shape[0]
         dtype = mlvl_feats[0].dtype
         bev_queries = self.bev_embedding.weight.to(dtype)
@@ -1078,5 +1089,7 @@ class BackwardProjection(BaseModule):
             bev_pos=bev_pos, img_metas=img_metas, cam_params=cam_params,
             gt_bboxes_3d=gt_bboxes_3d, pred_img_depth=pred_img_depth,
             prev_bev=None, bev_mask=bev_mask)
-        return bev.permute(0, 2, 1).view(bs, -1, self.bev_h,
-                                         self.bev_w).contiguous()
+        bev = bev.permute(0, 2, 1).view(bs, -1, self.bev_h, self.bev_w)
+        if out is not None:
+            return out.copy_(bev)
+        return bev.contiguous()

@@ -325,3 +325,66 @@ def test_training_gradients_reach_every_input(case, monkeypatch):
         hit = [n for n in grads_gpu if n.endswith(frag)]
         assert hit and float(grads_gpu[hit[0]].abs().max()) > 0, frag
     assert used > 10
+
+
+# ------------------------------------------------ full-size configurations --
+def _bp_inputs(B, E, levels, DC, bev, inp, seed=17):
+    from fbbev_b200 import synthetic
+    g = torch.Generator().manual_seed(seed)
+    cams = synthetic.make_cam_params(B, 6, inp, jitter=1.0, seed=seed)
+    mlvl = [torch.randn(B, 6, E, h, w, generator=g) for h, w in levels]
+    H0, W0 = levels[0]
+    depth = torch.randn(B, 6, DC, H0, W0, generator=g).softmax(2)
+    lss = torch.randn(B, E, *bev, generator=g) * 0.1
+    return cams, mlvl, depth, lss
+
+
+def _bp_vs_cpu_oracle(bp, cams, mlvl, depth, lss):
+    """GPU module (fused kernels through the C ABI) against the same module's
+    host logic around the oracle's attention cores (oracle/backward_ref.py:
+    the reference's re-batching algorithm, MSDA by the C oracle)."""
+    import copy
+    from oracle.backward_ref import backward_projection_cpu
+    with torch.no_grad():
+        got = bp(
+            [f.to(DEV) for f in mlvl], None, lss_bev=lss.to(DEV),
+            cam_params=[c.to(DEV) for c in cams], pred_img_depth=depth.to(DEV))
+    bp_cpu = copy.deepcopy(bp).cpu()
+    want = backward_projection_cpu(bp_cpu, mlvl, lss, list(cams), depth)
+    return got.cpu().numpy(), want.numpy()
+
+
+def test_backward_only_config_full_size():
+    """BASELINE.json configs[3] THROUGH the plugin: 200x200 BEV queries,
+    embed 256 (8 heads x 32 channels), 4 feature levels (32x88 ... 4x11),
+    8 points / 4 Z anchors, 80 depth bins: fbbev_msda_fused_fwd and
+    fbbev_da_sca_fwd at <32, 4> plus the tcgen05 Linears at K = N = 256."""
+    levels = [(32, 88), (16, 44), (8, 22), (4, 11)]
+    bev, inp = (200, 200), (512, 1408)
+    bp = _bp_module(bev, 256, levels, inp, 1)
+    cams, mlvl, depth, lss = _bp_inputs(1, 256, levels, 80, bev, inp)
+    got, want = _bp_vs_cpu_oracle(bp, cams, mlvl, depth, lss)
+    assert got.shape == (1, 256, 200, 200)
+    np.testing.assert_allclose(got, want, rtol=0, atol=ATOL)
+
+
+def test_sixteen_frame_config_full_size():
+    """BASELINE.json configs[2]: 16 frames (B = 16) of the FB-OCC R50 geometry
+    through BackwardProjection in ONE call (200x200 queries, E = 80), against
+    the CPU oracle; plus frame independence: frame b of
+    the batched call == the same frame run alone."""
+    levels = [(16, 44)]
+    bev, inp = (200, 200), (256, 704)
+    bp = _bp_module(bev, 80, levels, inp, 16)
+    cams, mlvl, depth, lss = _bp_inputs(16, 80, levels, 80, bev, inp)
+    got, want = _bp_vs_cpu_oracle(bp, cams, mlvl, depth, lss)
+    assert got.shape == (16, 80, 200, 200)
+    np.testing.assert_allclose(got, want, rtol=0, atol=ATOL)
+    for b in (0, 9, 15):
+        with torch.no_grad():
+            one = bp([f[b:b + 1].to(DEV) for f in mlvl], None,
+                     lss_bev=lss[b:b + 1].to(DEV),
+                     cam_params=[c[b:b + 1].to(DEV) for c in cams],
+                     pred_img_depth=depth[b:b + 1].to(DEV))
+        np.testing.assert_allclose(one.cpu().numpy()[0], got[b], rtol=0,
+                                   atol=1e-5)

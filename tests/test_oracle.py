@@ -276,3 +276,48 @@ def test_prepare_oracle_vs_numpy_restatement_ragged(oracle_cpu, seed):
     np.testing.assert_array_equal(ln, lengths.astype(np.int32))
     np.testing.assert_array_equal(grd, rd.astype(np.int32))   # stable order
     np.testing.assert_array_equal(grf, rf.astype(np.int32))
+
+
+# ------------------------------------------- eager "reference on GPU" ------
+@pytest.mark.parametrize("case", ["b_bp_e80_1lvl", "b_bp_e64_3lvl"])
+def test_eager_reference_restatement_vs_golden(case):
+    """oracle/gpu_ref.py (the comparator bench.py times as "the reference on
+    the same B200") reproduces the reference's own recorded outputs: the
+    backward projection with the re-batching cross-attention and the
+    grid_sample MSDA, and voxel_pooling_prepare_v2 op for op.  Device-agnostic
+    torch ops, so it is pinned here on the CPU."""
+    import torch
+    from bp_common import build_bp, cam_params
+    from oracle import gpu_ref
+    g, bp = build_bp(case, "cpu")
+    n_lvl = len(g["level_shapes"])
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    mlvl = [tt(g[f"feat{i}"]) for i in range(n_lvl)]
+    with torch.no_grad(), gpu_ref.eager_reference_mode(bp.transformer.encoder):
+        out = bp(mlvl, None, lss_bev=tt(g["lss_bev"]),
+                 cam_params=cam_params(g, "cpu"), pred_img_depth=tt(g["depth"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["f_small_6cam", "f_unit_1cam",
+                                  "f_negative_trunc"])
+def test_eager_prepare_restatement_vs_golden(case):
+    import torch
+    from oracle import gpu_ref
+    g = load_golden(case)
+    rb, rd, rf, st, ln = gpu_ref.voxel_pooling_prepare_v2(
+        torch.from_numpy(g["coor"]), torch.from_numpy(g["grid_lower_bound"]),
+        torch.from_numpy(g["grid_interval"]), torch.from_numpy(g["grid_size"]))
+    assert np.array_equal(rb.numpy(), g["ranks_bev"])
+    assert np.array_equal(st.numpy(), g["interval_starts"])
+    assert np.array_equal(ln.numpy(), g["interval_lengths"])
+    a = canon_index(rb.numpy(), rd.numpy(), rf.numpy())
+    b = canon_index(g["ranks_bev"], g["ranks_depth"], g["ranks_feat"])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    feat = torch.from_numpy(g["feat"]).permute(0, 1, 3, 4, 2).contiguous()
+    B, C, Y, X, Z = g["bev_feat"].shape
+    out = gpu_ref.bev_pool_v2_index_add(torch.from_numpy(g["depth"]), feat, rd,
+                                        rf, rb, (B, Z, Y, X, C))
+    np.testing.assert_allclose(out.permute(0, 1, 3, 4, 2).numpy(),
+                               g["bev_feat"], rtol=0, atol=1e-5)

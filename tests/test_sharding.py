@@ -39,6 +39,13 @@ def _worker(rank, world, port, q):
     out = local * 2 + 1
     full = gather_bev(out)
     ok = torch.equal(full, frames * 2 + 1)
+    # zero-copy hand-off: the producer writes into its slot of the gather
+    # buffer, the collective runs in place
+    from fbbev_b200.sharding import GatherBuffer
+    buf = GatherBuffer(2, 3, 5, 6, "cpu")
+    assert buf.slot.data_ptr() == buf.full[rank * 2:].data_ptr()
+    buf.slot.copy_(local * 2 + 1)           # stands for forward(..., out=slot)
+    ok = ok and torch.equal(buf.gather(), frames * 2 + 1)
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok), tuple(full.shape)))
