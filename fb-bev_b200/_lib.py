@@ -49,14 +49,19 @@ _SIGNATURES = {
     "fbbev_point_sampling": (
         ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32] * 3 +
         [ctypes.c_float] * 4 + [_p] * 4),
+    "fbbev_bev_query_init": (ctypes.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "fbbev_msda_fwd": (ctypes.c_int, [_p] * 5 + [_i32] * 7 + [_p, _p]),
     "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
-    "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p, _p]),
-    "fbbev_da_sca_fwd": (ctypes.c_int, [_p] * 10 + [_i32] * 10 + [_p, _p]),
+    "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 8 + [_p, _p]),
+    "fbbev_da_sca_workspace_bytes": (_sz, [_i32, _i32]),
+    "fbbev_da_sca_fwd": (ctypes.c_int,
+                         [_p] * 10 + [_i32] * 10 + [_p, _p, _sz, _p]),
+    "fbbev_history_warp": (ctypes.c_int, [_p, _p] + [_i32] * 5 + [_p, _i32, _i32, _p]),
     "fbbev_linear_packed_bytes": (ctypes.c_size_t, [_i32, _i32]),
     "fbbev_linear_pack": (ctypes.c_int, [_p, _i32, _i32, _p, _p]),
     "fbbev_linear_fwd_split": (ctypes.c_int, [
-        _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
+        _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p,
+        _i64, _p]),
     "fbbev_linear_fwd": (ctypes.c_int, [
         _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i32,
         ctypes.c_float, _p, _i64, _p]),
@@ -113,7 +118,8 @@ class KernelTimer:
     _SKIP = ("fbbev_abi_version", "fbbev_debug_launch_count",
              "fbbev_error_string", "fbbev_linear_packed_bytes",
              "fbbev_bev_pool_v2_dense_workspace_bytes",
-             "fbbev_voxel_prepare_workspace_bytes")
+             "fbbev_voxel_prepare_workspace_bytes",
+             "fbbev_da_sca_workspace_bytes")
 
     def __init__(self):
         self.records = []   # (name, args, start_event, end_event)

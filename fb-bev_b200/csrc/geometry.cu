@@ -70,9 +70,57 @@ __global__ void __launch_bounds__(256) point_sampling_kernel(
   mask[i] = m ? 1 : 0;
 }
 
+// bev_queries[b, q, :] = embedding[q, :] + lss_bev[b, :, q]
+//   backward_projection.py:93-97: bev_embedding.weight.unsqueeze(1).repeat(1, bs, 1)
+//   + lss_bev.flatten(2).permute(2, 0, 1), as ONE pass producing the
+//   (bs, nq, E)-contiguous tensor the encoder works on (the reference-shaped
+//   (nq, bs, E) tensor is its permuted view).  The (E, nq) -> (nq, E) transpose
+//   of lss_bev goes through a padded shared-memory tile so that both the read
+//   and the write are coalesced.
+__global__ void __launch_bounds__(256) bev_query_init_kernel(
+    const float* __restrict__ emb, const float* __restrict__ lss, int bs, int nq,
+    int E, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int q0 = blockIdx.x * 32, e0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (lss) {
+    const float* src = lss + (int64_t)b * E * nq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + ty + 8 * i, q = q0 + tx;
+      tile[ty + 8 * i][tx] = (e < E && q < nq) ? __ldg(src + (int64_t)e * nq + q)
+                                               : 0.f;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + ty + 8 * i, e = e0 + tx;
+    if (q < nq && e < E) {
+      float v = __ldg(emb + (int64_t)q * E + e);
+      if (lss) v = __fadd_rn(v, tile[tx][ty + 8 * i]);
+      out[((int64_t)b * nq + q) * E + e] = v;
+    }
+  }
+}
+
 }  // namespace fbbev
 
 using namespace fbbev;
+
+FBBEV_API int fbbev_bev_query_init(const float* embedding, const float* lss_bev,
+                                   int32_t bs, int32_t nq, int32_t E, float* out,
+                                   fbbev_stream_t stream) {
+  if (bs <= 0 || nq <= 0 || E <= 0 || !embedding || !out)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (bs > 65535 || (E + 31) / 32 > 65535) return FBBEV_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)((nq + 31) / 32), (unsigned)((E + 31) / 32),
+                  (unsigned)bs);
+  count_launch();
+  bev_query_init_kernel<<<grid, 256, 0, as_stream(stream)>>>(embedding, lss_bev,
+                                                              bs, nq, E, out);
+  return launch_status();
+}
 
 FBBEV_API int fbbev_point_sampling(
     const float* X, const float* Y, const float* Z, int32_t nX, int32_t nY,

@@ -194,6 +194,7 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, int n, int k,
 // -------------------------------- the kernel ---------------------------------
 struct LinearParams {
   const float* x;         // [M][K]
+  const float* x_add;     // [M][K] or null: the GEMM input is x + x_add
   const float* wp;        // packed weights
   const float* bias;      // [N] or null
   const float* residual;  // [M][N] or null
@@ -203,6 +204,7 @@ struct LinearParams {
   int M, K, N, npad, n_kb, relu, rows_per_cta, stages;
   int slab_pitch;  // floats per slab row: 20 (16-column chunks) or N + 4 (whole rows)
   int64_t ldx, ldr, ldy;  // row strides in floats
+  int64_t ldxa;           // row stride of x_add
   // optional second output: columns [n_split, N) go to y2 (row stride ldy2)
   float* y2;
   int64_t ldy2;
@@ -295,6 +297,23 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           v[u][i] = ok ? __ldg(reinterpret_cast<const float4*>(
                              (i < 5 ? b0 : b1) + 8 * cp))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.x_add) {  // query + query_pos in the loader (one fp32 add, as torch)
+          const float* a0 = p.x_add + (size_t)g0 * p.ldxa + col0;
+          const float* a1 = a0 + (size_t)16 * p.ldxa;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int cp = i % 5;
+            const bool ok = (i < 5 ? ok0 : ok1) && col0 + 8 * cp < p.K;
+            if (ok) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(
+                  (i < 5 ? a0 : a1) + 8 * cp));
+              v[u][i].x = __fadd_rn(v[u][i].x, a.x);
+              v[u][i].y = __fadd_rn(v[u][i].y, a.y);
+              v[u][i].z = __fadd_rn(v[u][i].z, a.z);
+              v[u][i].w = __fadd_rn(v[u][i].w, a.w);
+            }
+          }
         }
       }
       if (threadIdx.x == 128) TRACE(1, 100 + w0);
@@ -660,8 +679,8 @@ FBBEV_API int fbbev_linear_pack(const float* weight, int32_t n, int32_t k,
   return launch_status();
 }
 
-static int linear_run(const float* x, int64_t ldx, const float* packed,
-                      const float* bias, const float* residual, int64_t ldr,
+static int linear_run(const float* x, int64_t ldx, const float* x_add,
+                      int64_t ldxa, const float* packed, const float* bias, const float* residual, int64_t ldr,
                       const float* ln_weight, const float* ln_bias, int64_t m,
                       int32_t k, int32_t n, int32_t relu, float ln_eps, float* y,
                       int64_t ldy, float* y2, int64_t ldy2, int32_t n_split,
@@ -681,11 +700,13 @@ static int linear_run(const float* x, int64_t ldx, const float* packed,
     return FBBEV_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
        reinterpret_cast<uintptr_t>(packed) |
-       reinterpret_cast<uintptr_t>(residual)) & 15)
+       reinterpret_cast<uintptr_t>(residual) |
+       reinterpret_cast<uintptr_t>(x_add)) & 15)
     return FBBEV_ERR_INVALID_ARGUMENT;
+  if (x_add && (ldxa < k || ldxa % 4)) return FBBEV_ERR_INVALID_ARGUMENT;
   if (m == 0) return FBBEV_OK;
   LinearParams p;
-  p.x = x; p.wp = packed; p.bias = bias; p.residual = residual;
+  p.x = x; p.x_add = x_add; p.ldxa = ldxa; p.wp = packed; p.bias = bias; p.residual = residual;
   p.gamma = ln_weight; p.beta = ln_bias; p.y = y;
   p.y2 = y2; p.ldy2 = ldy2; p.n_split = n_split;
   p.M = (int)m; p.K = k; p.N = n; p.npad = pad16(n); p.n_kb = n_kblocks(k);
@@ -732,16 +753,18 @@ FBBEV_API int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
                                const float* ln_bias, int64_t m, int32_t k,
                                int32_t n, int32_t relu, float ln_eps, float* y,
                                int64_t ldy, fbbev_stream_t stream) {
-  return linear_run(x, ldx, packed, bias, residual, ldr, ln_weight, ln_bias, m, k,
-                    n, relu, ln_eps, y, ldy, nullptr, 0, n, stream);
+  return linear_run(x, ldx, nullptr, 0, packed, bias, residual, ldr, ln_weight,
+                    ln_bias, m, k, n, relu, ln_eps, y, ldy, nullptr, 0, n, stream);
 }
 
 FBBEV_API int fbbev_linear_fwd_split(const float* x, int64_t ldx,
+                                     const float* x_add, int64_t ldx_add,
                                      const float* packed, const float* bias,
                                      int64_t m, int32_t k, int32_t n,
                                      int32_t n_split, int32_t relu, float* y0,
                                      int64_t ldy0, float* y1, int64_t ldy1,
                                      fbbev_stream_t stream) {
-  return linear_run(x, ldx, packed, bias, nullptr, 0, nullptr, nullptr, m, k, n,
-                    relu, 0.f, y0, ldy0, y1, ldy1, n_split, stream);
+  return linear_run(x, ldx, x_add, ldx_add, packed, bias, nullptr, 0, nullptr,
+                    nullptr, m, k, n, relu, 0.f, y0, ldy0, y1, ldy1, n_split,
+                    stream);
 }

@@ -23,7 +23,11 @@
 // streamed operands only -- which the two fused entry points shrink further by
 // never materialising sampling_locations / normalised weights / the one-hot
 // depth tensor.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "da_sca_smem.h"
+#include "msda_common.cuh"
 
 namespace fbbev {
 
@@ -51,6 +55,30 @@ __device__ __forceinline__ void load_vec<1>(const float* p, float* v) {
   v[0] = __ldg(p);
 }
 
+// Ten contiguous floats whose address is 8-byte but not always 16-byte aligned
+// (head width 10: the chunk of head m starts 40 m bytes into the pixel): three
+// loads -- 128 + 128 + 64 bits when the start is 16-byte aligned, 64 + 128 + 128
+// otherwise -- instead of five 64-bit ones.  The gathers of these kernels are
+// bound by L1 wavefronts (one per distinct line per load instruction), so two
+// fewer instructions per 40-byte chunk is 40 % less L1 work.
+__device__ __forceinline__ void load10(const float* p, float (&v)[10]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    const float2 c = __ldg(reinterpret_cast<const float2*>(p + 8));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y;
+  } else {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 2));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p + 6));
+    v[0] = a.x; v[1] = a.y;
+    v[2] = b.x; v[3] = b.y; v[4] = b.z; v[5] = b.w;
+    v[6] = c.x; v[7] = c.y; v[8] = c.z; v[9] = c.w;
+  }
+}
+
 // acc[0..CH) += wgt * bilinear(value_level, h_im, w_im) for one head.
 // `val` points at element [pixel 0][head m][channel 0] of the level; pixel
 // stride is E = heads * ch floats.
@@ -73,6 +101,22 @@ __device__ __forceinline__ void sample_accum(const float* __restrict__ val,
   const float* p2 = p1 + E;
   const float* p3 = p1 + (int64_t)W * E;
   const float* p4 = p3 + E;
+  if (CH == 10 && (E & 1) == 0 &&
+      (reinterpret_cast<uintptr_t>(val) & 7) == 0) {
+    float v1[10], v2[10], v3[10], v4[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v1[k] = v2[k] = v3[k] = v4[k] = 0.f;
+    if (t && l) load10(p1, v1);
+    if (t && r) load10(p2, v2);
+    if (btm && l) load10(p3, v3);
+    if (btm && r) load10(p4, v4);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float s = w1 * v1[k] + w2 * v2[k] + w3 * v3[k] + w4 * v4[k];
+      acc[k] += s * wgt;
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < CH; c += VW) {
     float v1[VW], v2[VW], v3[VW], v4[VW];
@@ -88,33 +132,6 @@ __device__ __forceinline__ void sample_accum(const float* __restrict__ val,
       acc[c + k] += s * wgt;
     }
   }
-}
-
-// scalar bilinear (depth look-up): value laid out [pixel][stride] floats
-__device__ __forceinline__ float sample_scalar(const float* __restrict__ val,
-                                               int H, int W, int stride,
-                                               float h_im, float w_im) {
-  if (!(h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W))
-    return 0.f;
-  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-  const int h_high = h_low + 1, w_high = w_low + 1;
-  const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
-  const float hh = 1.f - lh, hw = 1.f - lw;
-  const float* p1 = val + ((int64_t)h_low * W + w_low) * stride;
-  float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
-  if (h_low >= 0 && w_low >= 0) v1 = __ldg(p1);
-  if (h_low >= 0 && w_high <= W - 1) v2 = __ldg(p1 + stride);
-  if (h_high <= H - 1 && w_low >= 0) v3 = __ldg(p1 + (int64_t)W * stride);
-  if (h_high <= H - 1 && w_high <= W - 1)
-    v4 = __ldg(p1 + (int64_t)W * stride + stride);
-  const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-  return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
-}
-
-// pixel coordinate of a normalised location: loc * size - 0.5, product rounded
-// to fp32 before the subtraction exactly as in mmcv's kernel (no FMA contraction)
-__device__ __forceinline__ float pix(float loc, int size) {
-  return __fsub_rn(__fmul_rn(loc, (float)size), 0.5f);
 }
 
 template <int CH>
@@ -206,15 +223,32 @@ __device__ __forceinline__ void softmax_stats(const float* __restrict__ lg,
 }
 
 // ---------------- fused mmcv MultiScaleDeformableAttention core ------------
-template <int CH>
-__global__ void __launch_bounds__(kMsdaThreads) msda_fused_fwd_kernel(
+// PATCH > 0: self-attention over the BEV map itself (one level, one query per
+// value pixel).  A block then owns a PATCH x PATCH_Y patch of queries instead of
+// a run of a BEV row: every query samples within a few pixels of itself, so the
+// square's footprint in `value` is ~4x smaller than a row segment's and stays
+// in L1 (ncu on the row mapping: 75 % L1 hit rate, 133 MB of L2 sectors for a
+// 12.8 MB map -- the kernel was bound by L2 gathers).
+template <int CH, int PATCH, int PATCH_Y>
+__global__ void __launch_bounds__(PATCH > 0 ? PATCH * PATCH_Y * 8 : kMsdaThreads)
+    msda_fused_fwd_kernel(
     const float* __restrict__ value, const int64_t* __restrict__ shapes,
     const int64_t* __restrict__ lstart, const float* __restrict__ ref,
     const float* __restrict__ offsets, const float* __restrict__ logits,
     int64_t n_items, int n_value, int heads, int levels, int nq, int points,
-    float* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_items) return;
+    int patch_w, float* __restrict__ out) {
+  int64_t idx;
+  if (PATCH > 0) {
+    // heads == 8; grid = (patches_x, patches_y, bs)
+    const int m = threadIdx.x & 7, ql = threadIdx.x >> 3;
+    const int qx = blockIdx.x * PATCH + ql % PATCH;
+    const int qy = blockIdx.y * PATCH_Y + ql / PATCH;
+    if (qx >= patch_w || qy * patch_w + qx >= nq) return;
+    idx = ((int64_t)blockIdx.z * nq + (int64_t)qy * patch_w + qx) * heads + m;
+  } else {
+    idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_items) return;
+  }
   const int m = (int)(idx % heads);
   const int64_t bq = idx / heads;
   const int b = (int)(bq / nq);
@@ -352,6 +386,11 @@ __global__ void __launch_bounds__(kMsdaThreads) da_sca_fwd_kernel(
 
 using namespace fbbev;
 
+FBBEV_API size_t fbbev_da_sca_workspace_bytes(int32_t bs, int32_t n_cams) {
+  if (bs <= 0 || n_cams <= 0) return 0;
+  return da_sca_smem_workspace_bytes(bs, n_cams);
+}
+
 FBBEV_API int fbbev_msda_fwd(const float* value, const int64_t* spatial_shapes,
                              const int64_t* level_start, const float* loc,
                              const float* attw, int32_t bs, int32_t n_value,
@@ -390,10 +429,10 @@ FBBEV_API int fbbev_msda_fused_fwd(
     const float* value, const int64_t* spatial_shapes,
     const int64_t* level_start, const float* ref, const float* offsets,
     const float* logits, int32_t bs, int32_t n_value, int32_t heads,
-    int32_t ch, int32_t levels, int32_t nq, int32_t points, float* out,
-    fbbev_stream_t stream) {
+    int32_t ch, int32_t levels, int32_t nq, int32_t points, int32_t patch_w,
+    float* out, fbbev_stream_t stream) {
   if (bs < 0 || nq < 0 || n_value <= 0 || heads <= 0 || ch <= 0 ||
-      levels <= 0 || points <= 0)
+      levels <= 0 || points <= 0 || patch_w < 0)
     return FBBEV_ERR_INVALID_ARGUMENT;
   const int64_t n_items = (int64_t)bs * nq * heads;
   if (n_items == 0) return FBBEV_OK;
@@ -403,10 +442,37 @@ FBBEV_API int fbbev_msda_fused_fwd(
   const unsigned grid = (unsigned)ceil_div64(n_items, kMsdaThreads);
   cudaStream_t st = as_stream(stream);
   count_launch();
+  if (patch_w > 0 && heads == 8 && levels == 1 && nq == n_value &&
+      nq % patch_w == 0) {
+    // BEV self-attention: square query patches (see the kernel)
+    static int py = -1;  // FBBEV_MSDA_PATCH_Y: tuning aid (8 or 4 rows)
+    if (py < 0) {
+      const char* e = getenv("FBBEV_MSDA_PATCH_Y");
+      py = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    constexpr int kPatch = 8;
+    const int rows = nq / patch_w;
+    const dim3 pgrid((unsigned)((patch_w + kPatch - 1) / kPatch),
+                     (unsigned)((rows + py - 1) / py), (unsigned)bs);
+    if (pgrid.y <= 65535 && pgrid.z <= 65535) {
 #define FBBEV_LAUNCH(CHV)                                                    \
-  msda_fused_fwd_kernel<CHV><<<grid, kMsdaThreads, 0, st>>>(                 \
+  if (py == 8)                                                               \
+    msda_fused_fwd_kernel<CHV, kPatch, 8><<<pgrid, kPatch * 64, 0, st>>>(    \
+        value, spatial_shapes, level_start, ref, offsets, logits, n_items,   \
+        n_value, heads, levels, nq, points, patch_w, out);                   \
+  else                                                                       \
+    msda_fused_fwd_kernel<CHV, kPatch, 4><<<pgrid, kPatch * 32, 0, st>>>(    \
+        value, spatial_shapes, level_start, ref, offsets, logits, n_items,   \
+        n_value, heads, levels, nq, points, patch_w, out)
+      FBBEV_CH_DISPATCH(ch, FBBEV_LAUNCH)
+#undef FBBEV_LAUNCH
+      return launch_status();
+    }
+  }
+#define FBBEV_LAUNCH(CHV)                                                    \
+  msda_fused_fwd_kernel<CHV, 0, 0><<<grid, kMsdaThreads, 0, st>>>(              \
       value, spatial_shapes, level_start, ref, offsets, logits, n_items,     \
-      n_value, heads, levels, nq, points, out)
+      n_value, heads, levels, nq, points, 0, out)
   FBBEV_CH_DISPATCH(ch, FBBEV_LAUNCH)
 #undef FBBEV_LAUNCH
   return launch_status();
@@ -419,7 +485,7 @@ FBBEV_API int fbbev_da_sca_fwd(
     const int64_t* level_start, const float* dbound_host, int32_t bs,
     int32_t n_cams, int32_t nq, int32_t n_value, int32_t heads, int32_t ch,
     int32_t levels, int32_t points, int32_t Z, int32_t DC, float* out,
-    fbbev_stream_t stream) {
+    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
   if (bs < 0 || nq < 0 || n_cams <= 0 || n_value <= 0 || heads <= 0 ||
       ch <= 0 || levels <= 0 || points <= 0 || Z <= 0 || DC <= 0 ||
       !dbound_host || points % Z != 0)
@@ -436,6 +502,15 @@ FBBEV_API int fbbev_da_sca_fwd(
   P.heads = heads; P.levels = levels; P.points = points; P.DC = DC;
   const unsigned grid = (unsigned)ceil_div64(n_items, kMsdaThreads);
   cudaStream_t st = as_stream(stream);
+  // whole camera map in shared memory when it fits (da_sca_smem.cu)
+  if (workspace && workspace_bytes >= da_sca_smem_workspace_bytes(bs, n_cams) &&
+      da_sca_smem_eligible(n_cams, n_value, heads, ch, levels, points, Z) &&
+      bs * n_cams <= 4096 && (reinterpret_cast<uintptr_t>(value) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    return da_sca_smem_launch(value, depth_prob, ref_cam, ref_depth, mask,
+                              offsets, logits, spatial_shapes, P.d_min,
+                              P.d_step, bs, n_cams, nq, n_value, DC, out,
+                              workspace, st);
   count_launch();
 #define FBBEV_LAUNCH_Z(CHV, ZV)                                              \
   da_sca_fwd_kernel<CHV, ZV><<<grid, kMsdaThreads, 0, st>>>(                 \

@@ -110,10 +110,20 @@ def linear_fused(x, weight, bias=None, relu=False, residual=None, ln_weight=None
     return y.view(*lead, n)
 
 
-def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache):
+def _rows(t, k):
+    """(-1, k) view of ``t`` usable by the kernels (dense rows, 16-byte
+    aligned), copying only when the layout demands it."""
+    t2 = t.reshape(-1, k)
+    if t2.stride(-1) != 1 or t2.stride(0) % 4 or t2.data_ptr() % 16:
+        t2 = t2.contiguous()
+    return t2
+
+
+def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache, x_add=None):
     """``(x @ weight_a.T + bias_a, x @ weight_b.T + bias_b)`` as ONE launch when
     both fit a column block (sampling_offsets + attention_weights of an
-    attention module: same input, one consumer kernel).
+    attention module: same input, one consumer kernel).  With ``x_add`` the
+    input is ``x + x_add`` (``query + query_pos``), added in the kernel's loader.
 
     ``cache`` is a dict owned by the calling module; it keeps the concatenated
     weight / bias, keyed by the parameters' storage and version counters."""
@@ -121,6 +131,8 @@ def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache):
     na, k = weight_a.shape
     nb = weight_b.shape[0]
     if na + nb > MAX_N or na % 4 or nb % 4 or (bias_a is None) != (bias_b is None):
+        if x_add is not None:
+            x = x + x_add
         return (linear_fused(x, weight_a, bias_a), linear_fused(x, weight_b, bias_b))
     key = tuple((t.data_ptr(), t._version) for t in
                 (weight_a, weight_b, bias_a, bias_b) if t is not None)
@@ -133,16 +145,20 @@ def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache):
         cache["pair"] = hit
     _, w, b = hit
     lead = x.shape[:-1]
-    x2 = x.reshape(-1, k)
-    if x2.stride(-1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
-        x2 = x2.contiguous()
+    x2 = _rows(x, k)
     m = x2.shape[0]
+    xa = None
+    if x_add is not None:
+        if x_add.shape != x.shape:
+            x_add = x_add.expand_as(x)
+        xa = _rows(x_add, k)
     ya = torch.empty((m, na), dtype=torch.float32, device=x.device)
     yb = torch.empty((m, nb), dtype=torch.float32, device=x.device)
     (_, _, buf), = _pack(w)
     L = _lib.lib()
     _lib.check(L.fbbev_linear_fwd_split(
-        _lib.ptr(x2), x2.stride(0), _lib.ptr(buf), _lib.ptr(b), m, k, na + nb, na,
-        0, _lib.ptr(ya), na, _lib.ptr(yb), nb, _lib.stream_ptr(x.device)),
-        "fbbev_linear_fwd_split")
+        _lib.ptr(x2), x2.stride(0), _lib.ptr(xa),
+        xa.stride(0) if xa is not None else 0, _lib.ptr(buf), _lib.ptr(b), m, k,
+        na + nb, na, 0, _lib.ptr(ya), na, _lib.ptr(yb), nb,
+        _lib.stream_ptr(x.device)), "fbbev_linear_fwd_split")
     return ya.view(*lead, na), yb.view(*lead, nb)

@@ -22,6 +22,7 @@ __all__ = ['MultiScaleDeformableAttnFunction_fp32',
            'ms_deform_attn_fused', 'ms_deform_attn_unfused',
            'da_spatial_cross_attention_core',
            'da_spatial_cross_attention_core_autograd', 'point_sampling',
+           'bev_query_init',
            'needs_grad']
 
 
@@ -106,13 +107,17 @@ MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction_fp32
 
 
 def ms_deform_attn_fused(value, spatial_shapes, level_start_index,
-                         reference_points, sampling_offsets, attention_logits):
+                         reference_points, sampling_offsets, attention_logits,
+                         map_width=0):
     """softmax + location arithmetic + sampling of mmcv
     ``MultiScaleDeformableAttention.forward`` in one kernel.
 
     value (bs, n_value, heads, ch); reference_points (bs, nq, levels, 2);
     sampling_offsets (bs, nq, heads, levels, points, 2) raw Linear output;
     attention_logits (bs, nq, heads, levels, points) raw Linear output.
+    ``map_width``: for self-attention over the map itself (one level, one
+    query per value pixel) the map's width -- a scheduling hint (square query
+    patches per block), results do not depend on it.
     Returns (bs, nq, heads*ch).  Forward only (inference path)."""
     dev = _lib.require_cuda(value, reference_points, sampling_offsets,
                             attention_logits)
@@ -128,14 +133,14 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index,
         rc = _lib.lib().fbbev_msda_fused_fwd(
             _lib.ptr(value), _lib.ptr(ss), _lib.ptr(ls), _lib.ptr(ref),
             _lib.ptr(off), _lib.ptr(lg), bs, n_value, heads, ch, levels, nq,
-            points, _lib.ptr(out), _lib.stream_ptr(dev))
+            points, int(map_width), _lib.ptr(out), _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_msda_fused_fwd')
     return out
 
 
 def ms_deform_attn_unfused(value, spatial_shapes, level_start_index,
                            reference_points, sampling_offsets,
-                           attention_logits, im2col_step=64):
+                           attention_logits, map_width=0, im2col_step=64):
     """Differentiable twin of :func:`ms_deform_attn_fused`: softmax and the
     sampling locations in PyTorch (as mmcv's module does), the sampling through
     ``MultiScaleDeformableAttnFunction_fp32`` (forward ``fbbev_msda_fwd``,
@@ -232,15 +237,39 @@ def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
     _, _, _, levels, points, _ = off.shape
     DC = depth_prob.shape[-1]
     out = value.new_empty((bs, nq, heads * ch))
+    L = _lib.lib()
+    ws_bytes = L.fbbev_da_sca_workspace_bytes(bs, n_cams)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.lib().fbbev_da_sca_fwd(
+        rc = L.fbbev_da_sca_fwd(
             _lib.ptr(value), _lib.ptr(depth_prob), _lib.ptr(ref),
             _lib.ptr(rdep), _lib.ptr(mask), _lib.ptr(off), _lib.ptr(lg),
             _lib.ptr(ss), _lib.ptr(ls), _lib.c_floats(dbound), bs, n_cams, nq,
             n_value, heads, ch, levels, points, Z, DC, _lib.ptr(out),
-            _lib.stream_ptr(dev))
+            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_da_sca_fwd')
     return out
+
+
+def bev_query_init(embedding, lss_bev):
+    """``embedding[:, None] + lss_bev.flatten(2).permute(2, 0, 1)`` of
+    BackwardProjection.forward (backward_projection.py:93-97) in one pass
+    (``fbbev_bev_query_init``).  embedding (nq, E); lss_bev (bs, E, h, w).
+    Returns the (nq, bs, E) tensor of the reference as a view of a
+    (bs, nq, E)-contiguous buffer."""
+    dev = _lib.require_cuda(embedding, lss_bev)
+    emb = embedding.detach().contiguous().float()
+    lss = lss_bev.contiguous().float()
+    bs, E = lss.shape[:2]
+    nq = emb.shape[0]
+    assert emb.shape[1] == E and lss[0, 0].numel() == nq
+    out = torch.empty((bs, nq, E), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fbbev_bev_query_init(
+            _lib.ptr(emb), _lib.ptr(lss), bs, nq, E, _lib.ptr(out),
+            _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_bev_query_init')
+    return out.permute(1, 0, 2)
 
 
 def point_sampling(axes, inv_bda, trans, ego2cam, post_rots, post_trans,

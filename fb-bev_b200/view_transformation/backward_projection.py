@@ -64,6 +64,7 @@ __all__ = ['BackwardProjection', 'BEVFormer', 'bevformer_encoder',
 
 
 _CONST_CACHE = {}
+_SIDE_STREAMS = {}  # one side stream per device (module-level: not deep-copied)
 
 
 def _const_tensor(values, device):
@@ -115,14 +116,17 @@ def _linear(mod, x, relu=False, residual=None, norm=None):
         eps=1e-5 if norm is None else norm.eps)
 
 
-def _linear_pair(owner, mod_a, mod_b, x):
-    """``(mod_a(x), mod_b(x))`` for two nn.Linears on the same input, one launch
-    when their widths allow; set ``FBBEV_LINEAR_PAIR=0`` for two launches."""
+def _linear_pair(owner, mod_a, mod_b, x, x_add=None):
+    """``(mod_a(x + x_add), mod_b(x + x_add))`` for two nn.Linears on the same
+    input, one launch when their widths allow (the addition happens in the
+    kernel's loader); set ``FBBEV_LINEAR_PAIR=0`` for two launches."""
     if (os.environ.get('FBBEV_LINEAR_PAIR', '1') == '1'
             and mod_a.weight.shape[1] % 4 == 0):
         return _linear_ops.linear_pair(
             x, mod_a.weight, mod_a.bias, mod_b.weight, mod_b.bias,
-            owner.__dict__.setdefault('_pair_cache', {}))
+            owner.__dict__.setdefault('_pair_cache', {}), x_add=x_add)
+    if x_add is not None:
+        x = x + x_add
     return _linear(mod_a, x), _linear(mod_b, x)
 
 
@@ -299,22 +303,26 @@ class MultiScaleDeformableAttention(BaseModule):
             value = query
         if identity is None:
             identity = query
-        if query_pos is not None:
+        fused = _fused_linear_on(query, self.dropout)
+        if query_pos is not None and not fused:
             query = query + query_pos
         if not self.batch_first:
             query = query.permute(1, 0, 2)
             value = value.permute(1, 0, 2)
+            if query_pos is not None and fused:
+                query_pos = query_pos.permute(1, 0, 2)
         bs, num_query, _ = query.shape
         _, num_value, _ = value.shape
-        fused = _fused_linear_on(query, self.dropout)
         lin = _linear if fused else (lambda m, x: m(x))
         value = lin(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
         if fused:
+            # query + query_pos is formed in the Linear's loader
             offsets, logits = _linear_pair(self, self.sampling_offsets,
-                                           self.attention_weights, query)
+                                           self.attention_weights, query,
+                                           x_add=query_pos)
         else:
             offsets = self.sampling_offsets(query)
             logits = self.attention_weights(query)
@@ -330,7 +338,8 @@ class MultiScaleDeformableAttention(BaseModule):
         core = ms_deform_attn_unfused if needs_grad(value, offsets, logits) \
             else ms_deform_attn_fused
         output = core(value, spatial_shapes, level_start_index,
-                      reference_points, offsets, logits)
+                      reference_points, offsets, logits,
+                      map_width=kwargs.get('bev_w') or 0)
         if fused:
             res = identity if self.batch_first else identity.permute(1, 0, 2)
             output = _linear(self.output_proj, output, residual=res,
@@ -406,12 +415,15 @@ class DA_MSDeformableAttention(BaseModule):
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         return value.view(bs, num_value, self.num_heads, -1)
 
-    def project_query(self, query):
+    def project_query(self, query, query_pos=None):
         bs, num_query, _ = query.shape
         if _fused_linear_on(query):
             offsets, logits = _linear_pair(self, self.sampling_offsets,
-                                           self.attention_weights, query)
+                                           self.attention_weights, query,
+                                           x_add=query_pos)
         else:
+            if query_pos is not None:
+                query = query + query_pos
             offsets = self.sampling_offsets(query)
             logits = self.attention_weights(query)
         offsets = offsets.view(
@@ -534,9 +546,14 @@ class DA_SpatialCrossAttention(BaseModule):
         if value is None:
             value = key
         inp_residual = query if residual is None else residual
-        if query_pos is not None:
-            query = query + query_pos.float()
+        # work the encoder started on its side stream (camera geometry, this
+        # module's value projection) must have finished before it is consumed
+        side_event = kwargs.get('side_event')
+        if side_event is not None and query.is_cuda:
+            torch.cuda.current_stream(query.device).wait_event(side_event)
         if bev_mask is not None:
+            if query_pos is not None:
+                query = query + query_pos.float()
             return self._forward_rebatch(
                 query, value, inp_residual, key_padding_mask, spatial_shapes,
                 reference_points_cam, level_start_index, bev_query_depth,
@@ -545,12 +562,11 @@ class DA_SpatialCrossAttention(BaseModule):
         da = self.deformable_attention
         B, N, DC, H, W = pred_img_depth.shape
         depth_prob = pred_img_depth.reshape(B * N, DC, H * W).permute(0, 2, 1)
-        num_cams, n_value, bs, E = value.shape
-        value = value.permute(2, 0, 1, 3).reshape(bs * num_cams, n_value, E)
-        # key_padding_mask is NOT forwarded: the reference's call of the
-        # deformable attention omits it (spatial_cross_attention_depth.py:201-206)
-        v = da.project_value(value.float())
-        offsets, logits = da.project_query(query)
+        v = (kwargs.get('projected_values') or {}).get(id(self))
+        if v is None:
+            v = self.project_camera_value(value)
+        offsets, logits = da.project_query(
+            query, None if query_pos is None else query_pos.float())
         if bev_query_depth.dim() == 5:
             bev_query_depth = bev_query_depth[..., 0]
         core = da_spatial_cross_attention_core
@@ -561,6 +577,15 @@ class DA_SpatialCrossAttention(BaseModule):
             per_cam_mask_list, offsets, logits, spatial_shapes,
             level_start_index, self.dbound, da.num_Z_anchors)
         return self._finish(slots, inp_residual, post_norm)
+
+    def project_camera_value(self, value):
+        """value (num_cams, n_value, bs, E) -> value_proj(value) as
+        (bs * num_cams, n_value, heads, ch) (:188-191, :524-527).
+        key_padding_mask is NOT applied: the reference's call of the deformable
+        attention omits it (spatial_cross_attention_depth.py:201-206)."""
+        num_cams, n_value, bs, E = value.shape
+        value = value.permute(2, 0, 1, 3).reshape(bs * num_cams, n_value, E)
+        return self.deformable_attention.project_value(value.float())
 
     def _forward_rebatch(self, query, value, inp_residual, key_padding_mask,
                          spatial_shapes, reference_points_cam,
@@ -747,7 +772,7 @@ class BEVFormerEncoderLayer(MyCustomBaseTransformerLayer):
                     spatial_shapes=_const_tensor(((bev_h, bev_w),),
                                                  query.device),
                     level_start_index=_const_tensor((0,), query.device),
-                    post_norm=fold, **kwargs)
+                    post_norm=fold, bev_w=bev_w, **kwargs)
                 attn_index += 1
                 identity = query
                 skip_norm = fold is not None
@@ -803,6 +828,15 @@ class bevformer_encoder(BaseModule):
     contract."""
 
     fused_geometry = os.environ.get('FBBEV_EXACT_GEOMETRY', '0') != '1'
+    # overlap the geometry / camera-value branch with the self-attention
+    side_stream = os.environ.get('FBBEV_SIDE_STREAM', '1') == '1'
+
+    @staticmethod
+    def _side(device):
+        key = str(device)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        return _SIDE_STREAMS[key]
 
     def __init__(self, *args, pc_range=None, grid_config=None,
                  data_config=None, return_intermediate=False,
@@ -941,8 +975,29 @@ class bevformer_encoder(BaseModule):
         ref_2d = cache[ck]
         if self.fused_geometry and bev_query.is_cuda:
             ref_3d = None  # only consumed by point_sampling
-            reference_points_cam, per_cam_mask_list, bev_query_depth = \
-                self.point_sampling_fused(cam_params)
+            if self.side_stream and not torch.is_grad_enabled() and \
+                    bev_mask is None:
+                # nothing before the first cross-attention depends on the
+                # camera geometry or on the projected camera features: run
+                # them (~25 small launches + one Linear) on a side stream
+                # beside the self-attention; the cross-attention waits on the
+                # event.  Also forks / joins correctly under CUDA-graph capture.
+                main = torch.cuda.current_stream(bev_query.device)
+                side = self._side(bev_query.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    reference_points_cam, per_cam_mask_list, bev_query_depth = \
+                        self.point_sampling_fused(cam_params)
+                    pv = {}
+                    for layer in self.layers:
+                        for att in layer.attentions:
+                            if isinstance(att, DA_SpatialCrossAttention):
+                                pv[id(att)] = att.project_camera_value(value)
+                    kwargs['projected_values'] = pv
+                    kwargs['side_event'] = side.record_event()
+            else:
+                reference_points_cam, per_cam_mask_list, bev_query_depth = \
+                    self.point_sampling_fused(cam_params)
         else:
             ref_3d = self.get_reference_points(
                 bev_h, bev_w, self.pc_range[5] - self.pc_range[2], dim='3d',
@@ -1076,9 +1131,14 @@ class BackwardProjection(BaseModule):
         bs = mlvl_feats[0].shape[0]
         dtype = mlvl_feats[0].dtype
         bev_queries = self.bev_embedding.weight.to(dtype)
-        bev_queries = bev_queries.unsqueeze(1).repeat(1, bs, 1)
-        if lss_bev is not None:
-            bev_queries = bev_queries + lss_bev.flatten(2).permute(2, 0, 1)
+        if (lss_bev is not None and lss_bev.is_cuda and dtype == torch.float32
+                and not needs_grad(bev_queries, lss_bev)):
+            # embedding + transposed lift-splat BEV in one kernel
+            bev_queries = _msda_ops.bev_query_init(bev_queries, lss_bev)
+        else:
+            bev_queries = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+            if lss_bev is not None:
+                bev_queries = bev_queries + lss_bev.flatten(2).permute(2, 0, 1)
         if bev_mask is not None:
             bev_mask = bev_mask.reshape(bs, -1)
         bev_pos = self.positional_encoding(

@@ -229,6 +229,18 @@ int fbbev_point_sampling(
     fbbev_stream_t stream);
 
 /*
+ * BEV queries of `BackwardProjection.forward`
+ *   .../backward_projection/backward_projection.py:93-97:
+ *   out[b, q, :] = embedding[q, :] + lss_bev[b, :, q]   (lss_bev may be NULL)
+ * embedding (nq, E) = bev_embedding.weight; lss_bev (bs, E, bev_h*bev_w) = the
+ * lift-splat BEV, channel-major; out (bs, nq, E) contiguous (the reference's
+ * (nq, bs, E) tensor is its permuted view).  One pass, one fp32 add per element.
+ */
+int fbbev_bev_query_init(const float* embedding, const float* lss_bev,
+                         int32_t bs, int32_t nq, int32_t E, float* out,
+                         fbbev_stream_t stream);
+
+/*
  * Drop-in for `ext_module.ms_deform_attn_forward` (mmcv-full 1.5.2 `_ext`)
  *   call site: .../backward_projection/bevformer_utils/
  *   multi_scale_deformable_attn_function.py:127-133.
@@ -264,13 +276,17 @@ int fbbev_msda_bwd(const float* value, const int64_t* spatial_shapes,
  * ref (bs,nq,levels,2); offsets (bs,nq,heads,levels,points,2) = raw output of
  * the sampling_offsets Linear; logits (bs,nq,heads,levels,points) = raw output
  * of the attention_weights Linear; out (bs,nq,heads*ch).
+ * patch_w: 0, or -- for self-attention over the map itself (levels == 1, nq ==
+ * n_value, 8 heads) -- the map width W: query q = y * W + x then sits on value
+ * pixel (y, x) and blocks own 8x8 query squares (L1-resident footprint) instead
+ * of runs of a row.  Results do not depend on it.
  */
 int fbbev_msda_fused_fwd(const float* value, const int64_t* spatial_shapes,
                          const int64_t* level_start, const float* ref,
                          const float* offsets, const float* logits, int32_t bs,
                          int32_t n_value, int32_t heads, int32_t ch,
                          int32_t levels, int32_t nq, int32_t points,
-                         float* out, fbbev_stream_t stream);
+                         int32_t patch_w, float* out, fbbev_stream_t stream);
 
 /*
  * Fused depth-aware spatial cross-attention: everything between the three
@@ -299,7 +315,19 @@ int fbbev_msda_fused_fwd(const float* value, const int64_t* spatial_shapes,
  * out        (bs, nq, heads*ch) = slots / clamp(count, 1), the tensor the
  *            reference feeds to output_proj (:219).
  * bev_mask (:156-159) is not supported by this entry point (NULL only).
+ *
+ * workspace (fbbev_da_sca_workspace_bytes(bs, n_cams) bytes, may be NULL):
+ * with it, and when one camera's value map fits in shared memory (n_value *
+ * heads * ch * 4 <= ~220 KB; 8 heads x 10 channels, 1 level, 8 points, 4
+ * anchors -- the FB-OCC head), the camera-resident kernel of da_sca_smem.cu
+ * runs: a CTA stages its camera's map with TMA bulk copies and serves the
+ * queries that camera sees from shared memory; contributions of several
+ * cameras to one query are combined with red.global.add on the zero-filled
+ * output (the order of these <= n_cams additions is not fixed).  Without a
+ * workspace, or for other shapes, the one-thread-per-(query, head) kernel
+ * gathers from global memory.
  */
+size_t fbbev_da_sca_workspace_bytes(int32_t bs, int32_t n_cams);
 int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
                      const float* ref_cam, const float* ref_depth,
                      const uint8_t* mask, const float* offsets,
@@ -307,7 +335,8 @@ int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
                      const int64_t* level_start, const float* dbound_host,
                      int32_t bs, int32_t n_cams, int32_t nq, int32_t n_value,
                      int32_t heads, int32_t ch, int32_t levels, int32_t points,
-                     int32_t Z, int32_t DC, float* out, fbbev_stream_t stream);
+                     int32_t Z, int32_t DC, float* out, void* workspace,
+                     size_t workspace_bytes, fbbev_stream_t stream);
 
 /* ---- row-wise Linear (+ bias, ReLU, residual, LayerNorm) on tcgen05 ---------
  * Replaces the nn.Linear / LayerNorm / residual chain of the reference's
@@ -347,12 +376,39 @@ int fbbev_linear_fwd(const float* x, int64_t ldx, const float* packed,
  * [0, n_split) go to y0 (row stride ldy0), [n_split, n) to y1 (ldy1), each dense.
  * This is sampling_offsets + attention_weights of both attention modules
  * (spatial_cross_attention_depth.py:420-424, 533-540): they act on the same
- * query and feed one sampling kernel.  No residual / LayerNorm here. */
-int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* packed,
+ * query and feed one sampling kernel.  No residual / LayerNorm here.
+ * x_add (may be NULL; row stride ldx_add): the GEMM input is x + x_add, formed
+ * in the loader with one fp32 add per element -- `query = query + query_pos`
+ * of both attention modules (spatial_cross_attention_depth.py:117-118, mmcv
+ * MultiScaleDeformableAttention.forward) without a separate pass. */
+int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* x_add,
+                           int64_t ldx_add, const float* packed,
                            const float* bias, int64_t m, int32_t k, int32_t n,
                            int32_t n_split, int32_t relu, float* y0,
                            int64_t ldy0, float* y1, int64_t ldy1,
                            fbbev_stream_t stream);
+
+/* =====================================================================
+ * T -- temporal fusion of the BEV / voxel history (the stage after the path)
+ * ===================================================================== */
+
+/*
+ * The sampling half of `FBOCC.fuse_history`
+ *   mmdet3d/models/fbbev/detectors/fbocc.py:207-319, `generate_grid` :170-205:
+ *   grid = rt_flow @ (x, y, z, 1); normalise; F.grid_sample(history, grid,
+ *   align_corners=True, bilinear, zeros); torch.cat([curr_bev, sampled], 1)
+ * as one pass.  history (n, mc, Z, H, W) fp32 = the T previous frames stacked
+ * along channels; flow (n, 4, 4) row-major = inverse(feat2bev) @ history_augs @
+ * curr_to_prev_ego_rt @ inverse(forward_augs) @ feat2bev (:196-197), mapping
+ * voxel indices (x, y, z, 1) of the current frame to voxel indices of the
+ * history; out (n, c_total, Z, H, W): the warped history is written into
+ * channels [ch_offset, ch_offset + mc) -- pass the concatenation buffer and
+ * ch_offset = C so that no torch.cat copy is needed.  The 5-D grid tensor is
+ * never materialised.
+ */
+int fbbev_history_warp(const float* history, const float* flow, int32_t n,
+                       int32_t mc, int32_t Z, int32_t H, int32_t W, float* out,
+                       int32_t c_total, int32_t ch_offset, fbbev_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ def _msda(value, shapes, lsi, loc, attw):
 
 
 def msda_fused_cpu(value, spatial_shapes, level_start_index, reference_points,
-                   sampling_offsets, attention_logits):
+                   sampling_offsets, attention_logits, map_width=0):
     """mmcv MultiScaleDeformableAttention.forward core: softmax, sampling
     locations = ref + offsets / (W, H), ms_deform_attn_forward."""
     shapes = spatial_shapes.cpu().long()

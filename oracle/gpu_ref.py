@@ -91,7 +91,8 @@ def bev_pool_v2_index_add(depth, feat_nhwc, ranks_depth, ranks_feat, ranks_bev,
 
 # --------------------------------------------------------------------- B ---
 def msda_fused_eager(value, spatial_shapes, level_start_index,
-                     reference_points, sampling_offsets, attention_logits):
+                     reference_points, sampling_offsets, attention_logits,
+                     map_width=0):
     """mmcv MultiScaleDeformableAttention.forward core with eager ops."""
     w = attention_logits.flatten(3).softmax(-1).view_as(attention_logits)
     wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)

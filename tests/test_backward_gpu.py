@@ -388,3 +388,71 @@ def test_sixteen_frame_config_full_size():
                      pred_img_depth=depth[b:b + 1].to(DEV))
         np.testing.assert_allclose(one.cpu().numpy()[0], got[b], rtol=0,
                                    atol=1e-5)
+
+
+@pytest.mark.parametrize("bs,nq,hw", [(1, 997, (16, 44)), (2, 4100, (8, 22)),
+                                      (3, 64, (4, 6))])
+def test_da_sca_smem_kernel_vs_global_kernel_and_oracle(bs, nq, hw):
+    """The camera-resident (shared-memory) cross-attention kernel against the
+    global-memory kernel of the same entry point and against the CPU oracle, on
+    random inputs with the awkward cases: a camera that sees nothing, queries
+    seen by 0 / 1 / 3+ cameras, reference points outside the image, ragged
+    query counts (not a multiple of 32)."""
+    from fbbev_b200 import _lib
+    from fbbev_b200.ops.ms_deform_attn import da_spatial_cross_attention_core
+    from oracle.backward_ref import da_sca_core_cpu
+    g = torch.Generator().manual_seed(31 + nq)
+    N, heads, ch, L, P, Z, DC = 6, 8, 10, 1, 8, 4, 40
+    H, W = hw
+    value = torch.randn(bs * N, H * W, heads, ch, generator=g)
+    depth_prob = torch.randn(bs * N, H * W, DC, generator=g).softmax(-1)
+    ref = torch.rand(N, bs, nq, Z, 2, generator=g) * 1.4 - 0.2
+    qdepth = torch.rand(N, bs, nq, Z, generator=g) * 50 - 2
+    mask = torch.rand(N, bs, nq, Z, generator=g) < 0.12
+    mask[3] = False                       # camera 3 sees nothing
+    mask[:, :, 5] = True                  # query 5: every camera but 3
+    mask[3, :, 5] = False
+    off = torch.randn(bs, nq, heads, L, P, 2, generator=g) * 2
+    lg = torch.randn(bs, nq, heads, L, P, generator=g)
+    ss = torch.tensor([[H, W]])
+    ls = torch.tensor([0])
+    dbound = [2.0, 42.0, 1.0]
+    want = da_sca_core_cpu(value, depth_prob, ref, qdepth, mask, off, lg, ss,
+                           ls, dbound, Z).numpy()
+    args = [a.to(DEV) for a in (value, depth_prob, ref, qdepth, mask, off, lg,
+                                ss, ls)]
+    launches0 = _lib.lib().fbbev_debug_launch_count()
+    got = da_spatial_cross_attention_core(*args, dbound, Z)
+    assert _lib.lib().fbbev_debug_launch_count() - launches0 == 2  # smem path
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-5)
+    # same entry point without a workspace -> global-memory kernel
+    L_ = _lib.lib()
+    out = torch.empty_like(got)
+    v, dp, r, qd, mk, o, l, s, lsi = args
+    rc = L_.fbbev_da_sca_fwd(
+        _lib.ptr(v), _lib.ptr(dp), _lib.ptr(r), _lib.ptr(qd),
+        _lib.ptr(mk.to(torch.uint8)), _lib.ptr(o), _lib.ptr(l), _lib.ptr(s),
+        _lib.ptr(lsi), _lib.c_floats(dbound), bs, N, nq, H * W, heads, ch, L, P,
+        Z, DC, _lib.ptr(out), None, 0, _lib.stream_ptr(torch.device(DEV)))
+    assert rc == 0
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=2e-5)
+    assert (out - got).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("bs,hw,E", [(1, (200, 200), 80), (3, (13, 7), 64),
+                                     (2, (5, 33), 20)])
+def test_bev_query_init_kernel(bs, hw, E):
+    """fbbev_bev_query_init == embedding.unsqueeze(1).repeat(1, bs, 1) +
+    lss_bev.flatten(2).permute(2, 0, 1) (backward_projection.py:93-97), bit for
+    bit (one fp32 add), ragged tile edges included."""
+    from fbbev_b200.ops.ms_deform_attn import bev_query_init
+    g = torch.Generator().manual_seed(bs * 7 + E)
+    nq = hw[0] * hw[1]
+    emb = torch.randn(nq, E, generator=g).to(DEV)
+    lss = torch.randn(bs, E, *hw, generator=g).to(DEV)
+    got = bev_query_init(emb, lss)
+    want = emb.unsqueeze(1).repeat(1, bs, 1) + lss.flatten(2).permute(2, 0, 1)
+    assert got.shape == want.shape == (nq, bs, E)
+    assert torch.equal(got, want)
+    assert got.permute(1, 0, 2).is_contiguous()

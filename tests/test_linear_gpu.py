@@ -125,3 +125,25 @@ def test_linear_widest_block():
             y = linear_fused(x, w, b, relu=True)
         ref = F.linear(x.double(), w.double(), b.double()).relu()
         assert (y.double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("m,k", [(40000, 80), (777, 80), (1000, 256)])
+def test_linear_pair_adds_position_in_loader(m, k):
+    """x_add: the GEMM input is x + x_add, formed in the kernel's loader
+    (`query + query_pos`): identical to adding first (one fp32 add per element,
+    then the same kernel), incl. a strided / broadcast x_add."""
+    from fbbev_b200.ops.linear import linear_pair, invalidate
+    g = torch.Generator(device="cuda").manual_seed(m)
+    x = torch.randn(m, k, device="cuda", generator=g)
+    pos_t = torch.randn(k, m, device="cuda", generator=g)      # channel-major
+    wa = torch.randn(64, k, device="cuda", generator=g) / k ** 0.5
+    wb = torch.randn(32, k, device="cuda", generator=g) / k ** 0.5
+    ba = torch.randn(64, device="cuda", generator=g)
+    bb = torch.randn(32, device="cuda", generator=g)
+    with torch.no_grad():
+        for pos in (pos_t.t().contiguous(), pos_t.t()):
+            ya, yb = linear_pair(x, wa, ba, wb, bb, {}, x_add=pos)
+            za, zb = linear_pair(x + pos, wa, ba, wb, bb, {})
+            assert torch.equal(ya, za) and torch.equal(yb, zb)
+    invalidate(wa)          # explicit cache-invalidation hook (EMA-style updates)
+    assert not hasattr(wa, "_fbbev_packed")
