@@ -877,6 +877,13 @@ def main():
         except Exception as ex:
             extra["reference_cuda"] = {"unavailable": str(ex)[:160]}
 
+    # ---- next stage: the history warp ----------------
+    if world == 1 and args.config == "fbocc200" and not args.no_reference_cuda:
+        try:
+            extra["fuse_history_warp"] = time_history_warp(dev, flush, peak)
+        except Exception as ex:
+            extra["fuse_history_warp"] = {"unavailable": str(ex)[:160]}
+
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -968,6 +975,57 @@ def frames16_block(world, rank, dev, flush, barrier, steps):
     del w16
     torch.cuda.empty_cache()
     return res
+
+
+def time_history_warp(dev, flush, peak):
+    """The sampling half of FBOCC.fuse_history at the shipped FB-OCC size
+    (16 history frames x 80 channels of 8 x 100 x 100 voxels, one sample):
+    fbbev_history_warp writing into the concatenation buffer against the
+    reference's op sequence (generate_grid matmul + F.grid_sample + torch.cat +
+    the history clone, fbocc.py:199-204, 275, 286, 311) on this GPU."""
+    from fbbev_b200.view_transformation.temporal_fusion import history_warp
+    from oracle.history_ref import history_warp_cpu
+    n, T, C, Z, H, W = 1, 16, 80, 8, 100, 100
+    g = torch.Generator(device=dev).manual_seed(5)
+    hist = torch.randn(n, T * C, Z, H, W, device=dev, generator=g)
+    curr = torch.randn(n, C, Z, H, W, device=dev, generator=g)
+    out = torch.empty(n, (T + 1) * C, Z, H, W, device=dev)
+    flow = torch.eye(4, device=dev)[None].clone()
+    flow[0, 0, 0], flow[0, 0, 1] = 0.9994, -0.0349   # 2 degrees of yaw
+    flow[0, 1, 0], flow[0, 1, 1] = 0.0349, 0.9994
+    flow[0, :3, 3] = torch.tensor([1.7, -0.6, 0.0])
+
+    def ev(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) * 1e3)
+        return statistics.median(ts)
+
+    def ours():
+        out[:, :C].copy_(curr)
+        history_warp(hist, flow, out, C)
+
+    def ref():
+        tmp = torch.empty(n, T * C, Z, H, W, device=dev)
+        history_warp_cpu(hist, flow, tmp, 0)        # grid matmul + grid_sample
+        cat = torch.cat([curr, tmp], 1)             # :286
+        return cat[:, :-C].detach().clone()         # :311
+    us, ref_us = ev(ours), ev(ref)
+    nbytes = 4 * (2 * hist.numel() + 2 * curr.numel())
+    return {"shape": "1 x (16 x 80) x 8 x 100 x 100", "ours_us": us,
+            "reference_eager_us": ref_us, "speedup": ref_us / us,
+            "algorithmic_bytes": nbytes,
+            "achieved_gbs": nbytes / (us * 1e-6) / 1e9,
+            "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak}
 
 
 def time_reference_gpu(w, idx, flush, our_step_ms):

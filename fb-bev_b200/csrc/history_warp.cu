@@ -35,6 +35,7 @@ struct WarpParams {
   const float* flow;   // (n, 4, 4) row-major, voxel index -> voxel index
   float* out;          // (n, C_total, Z, H, W); channels [ch_off, ch_off + MC)
   int n, MC, Z, H, W, C_total, ch_off;
+  int64_t hist_bstride;  // floats between samples of `hist`
 };
 
 __global__ void __launch_bounds__(kWarpThreads) history_warp_kernel(WarpParams P) {
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kWarpThreads) history_warp_kernel(WarpParams P
     wgt[k] = in ? w : 0.f;
     off[k] = in ? ((int64_t)zz * P.H + yy) * P.W + xx : 0;
   }
-  const float* src = P.hist + ((int64_t)b * P.MC + c0) * zhw;
+  const float* src = P.hist + (int64_t)b * P.hist_bstride + (int64_t)c0 * zhw;
   float* dst = P.out + ((int64_t)b * P.C_total + P.ch_off + c0) * zhw + v;
   const int nc = min(kChPerThread, P.MC - c0);
   for (int c = 0; c < nc; ++c) {
@@ -95,12 +96,14 @@ __global__ void __launch_bounds__(kWarpThreads) history_warp_kernel(WarpParams P
 
 using namespace fbbev;
 
-FBBEV_API int fbbev_history_warp(const float* history, const float* flow,
+FBBEV_API int fbbev_history_warp(const float* history,
+                                 int64_t history_batch_stride, const float* flow,
                                  int32_t n, int32_t mc, int32_t Z, int32_t H,
                                  int32_t W, float* out, int32_t c_total,
                                  int32_t ch_offset, fbbev_stream_t stream) {
   if (n < 0 || mc < 0 || Z <= 0 || H <= 0 || W <= 0 || c_total < mc ||
-      ch_offset < 0 || ch_offset + mc > c_total)
+      ch_offset < 0 || ch_offset + mc > c_total ||
+      history_batch_stride < (int64_t)mc * Z * H * W)
     return FBBEV_ERR_INVALID_ARGUMENT;
   if (n == 0 || mc == 0) return FBBEV_OK;
   if (!history || !flow || !out) return FBBEV_ERR_INVALID_ARGUMENT;
@@ -110,6 +113,7 @@ FBBEV_API int fbbev_history_warp(const float* history, const float* flow,
   P.hist = history; P.flow = flow; P.out = out;
   P.n = n; P.MC = mc; P.Z = Z; P.H = H; P.W = W;
   P.C_total = c_total; P.ch_off = ch_offset;
+  P.hist_bstride = history_batch_stride;
   const int64_t zhw = (int64_t)Z * H * W;
   const dim3 grid((unsigned)ceil_div64(zhw, kWarpThreads),
                   (unsigned)((mc + kChPerThread - 1) / kChPerThread),

@@ -3,3 +3,4 @@
 registers them (see ``registry.py``)."""
 from .forward_projection import *  # noqa: F401,F403
 from .backward_projection import *  # noqa: F401,F403
+from .temporal_fusion import *  # noqa: F401,F403

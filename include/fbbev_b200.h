@@ -398,7 +398,8 @@ int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* x_add,
  *   grid = rt_flow @ (x, y, z, 1); normalise; F.grid_sample(history, grid,
  *   align_corners=True, bilinear, zeros); torch.cat([curr_bev, sampled], 1)
  * as one pass.  history (n, mc, Z, H, W) fp32 = the T previous frames stacked
- * along channels; flow (n, 4, 4) row-major = inverse(feat2bev) @ history_augs @
+ * along channels, samples history_batch_stride floats apart (>= mc*Z*H*W: the
+ * history may be a channel slice of the previous step's concatenation buffer); flow (n, 4, 4) row-major = inverse(feat2bev) @ history_augs @
  * curr_to_prev_ego_rt @ inverse(forward_augs) @ feat2bev (:196-197), mapping
  * voxel indices (x, y, z, 1) of the current frame to voxel indices of the
  * history; out (n, c_total, Z, H, W): the warped history is written into
@@ -406,9 +407,10 @@ int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* x_add,
  * ch_offset = C so that no torch.cat copy is needed.  The 5-D grid tensor is
  * never materialised.
  */
-int fbbev_history_warp(const float* history, const float* flow, int32_t n,
-                       int32_t mc, int32_t Z, int32_t H, int32_t W, float* out,
-                       int32_t c_total, int32_t ch_offset, fbbev_stream_t stream);
+int fbbev_history_warp(const float* history, int64_t history_batch_stride,
+                       const float* flow, int32_t n, int32_t mc, int32_t Z,
+                       int32_t H, int32_t W, float* out, int32_t c_total,
+                       int32_t ch_offset, fbbev_stream_t stream);
 
 #ifdef __cplusplus
 }

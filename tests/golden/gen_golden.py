@@ -157,7 +157,107 @@ def gen_forward_2d(ref):
              seed=14)
 
 
+def load_fuse_history():
+    """FBOCC.fuse_history / generate_grid / generate_forward_transformation_matrix
+    (mmdet3d/models/fbbev/detectors/fbocc.py:37-42, 170-205, 207-319) compiled
+    from the reference file WHERE IT LIES: the module itself imports spconv,
+    cv2, mmdet ..., so the three function definitions are taken out of its AST
+    (decorators dropped: @force_fp32 is an fp32 cast) and executed as they are.
+    Nothing is copied into this repository."""
+    import ast
+    import torch.nn as nn
+    import torch.nn.functional as F
+    path = os.path.join(ref_import.REF, 'mmdet3d', 'models', 'fbbev',
+                        'detectors', 'fbocc.py')
+    tree = ast.parse(open(path).read())
+    want = {'generate_forward_transformation_matrix', 'generate_grid',
+            'fuse_history'}
+    nodes = [n for n in ast.walk(tree)
+             if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {n.name for n in nodes} == want
+    for n in nodes:
+        n.decorator_list = []
+    mod = ast.Module(body=nodes, type_ignores=[])
+    ns = {'torch': torch, 'F': F, 'nn': nn}
+    exec(compile(mod, path, 'exec'), ns)
+    return ns
+
+
+def gen_fuse_history():
+    """t_fuse_history.npz: four consecutive fuse_history calls of the
+    reference (first call, a normal step, a step where one sample starts a new
+    sequence, another normal step) on a small voxel grid."""
+    import types
+    import torch.nn as nn
+    from fbbev_b200.view_transformation.forward_projection import gen_dx_bx
+    ns = load_fuse_history()
+    C, T, Z, H, W, n = 4, 3, 3, 7, 6, 2
+    grid = dict(x=[-6, 6, 2.0], y=[-7, 7, 2.0], z=[-1, 5, 2.0])
+    dx, bx, nx = gen_dx_bx(grid['x'], grid['y'], grid['z'])
+    torch.manual_seed(77)
+    time_conv = nn.Sequential(nn.Conv3d(C + 1, C, 1), nn.SyncBatchNorm(C),
+                              nn.ReLU(inplace=True))
+    cat_conv = nn.Sequential(nn.Conv3d(C * (T + 1), C, 1), nn.SyncBatchNorm(C),
+                             nn.ReLU(inplace=True))
+    for seq in (time_conv, cat_conv):
+        bn = seq[1]
+        bn.running_mean.uniform_(-0.2, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.uniform_(-0.2, 0.2)
+        seq.eval()
+    me = types.SimpleNamespace(
+        history_bev=None, history_seq_ids=None, history_forward_augs=None,
+        history_sweep_time=None, history_cat_num=T, history_cam_sweep_freq=0.5,
+        interpolation_mode='bilinear', single_bev_num_channels=C,
+        do_history=True, history_keyframe_time_conv=time_conv,
+        history_keyframe_cat_conv=cat_conv,
+        forward_projection=types.SimpleNamespace(dx=dx, bx=bx, nx=nx))
+    me.generate_grid = lambda *a, **k: ns['generate_grid'](me, *a, **k)
+    g = torch.Generator().manual_seed(78)
+
+    def rigid(scale):
+        a = (torch.rand((), generator=g) - 0.5) * 0.3 * scale
+        m = torch.eye(4)
+        m[0, 0], m[0, 1], m[1, 0], m[1, 1] = a.cos(), -a.sin(), a.sin(), a.cos()
+        m[:3, 3] = (torch.rand(3, generator=g) - 0.5) * \
+            torch.tensor([3.0, 3.0, 0.5]) * scale
+        return m
+
+    arrays = dict(C=np.array(C), T=np.array(T), dx=_np(dx), bx=_np(bx),
+                  **{'sd_time::' + k: _np(v)
+                     for k, v in time_conv.state_dict().items()},
+                  **{'sd_cat::' + k: _np(v)
+                     for k, v in cat_conv.state_dict().items()})
+    seq_ids = [[5, 9], [5, 9], [5, 11], [5, 11]]
+    starts = [[True, True], [False, False], [False, True], [False, False]]
+    with torch.no_grad():
+        for step in range(4):
+            curr = torch.randn(n, C, H, W, Z, generator=g)
+            bda = torch.stack([rigid(1.0)[:3, :3] *
+                               (1.0 if i else -1.0) ** step for i in range(n)])
+            metas = [dict(sequence_group_idx=seq_ids[step][i],
+                          start_of_sequence=starts[step][i],
+                          curr_to_prev_ego_rt=rigid(1.0)) for i in range(n)]
+            out = ns['fuse_history'](me, curr, metas, bda)
+            arrays[f'curr{step}'] = _np(curr)
+            arrays[f'bda{step}'] = _np(bda)
+            arrays[f'c2p{step}'] = _np(torch.stack(
+                [m['curr_to_prev_ego_rt'] for m in metas]))
+            arrays[f'seq{step}'] = np.array(seq_ids[step])
+            arrays[f'start{step}'] = np.array(starts[step])
+            arrays[f'out{step}'] = _np(out)
+            # copies: the reference updates its state tensors in place later
+            arrays[f'history{step}'] = _np(me.history_bev).copy()
+            arrays[f'sweep{step}'] = _np(me.history_sweep_time).copy()
+    save('t_fuse_history', **arrays)
+
+
 def main():
+    if os.environ.get("GOLDEN_ONLY", "") == "fuse":
+        ref_import.install_stubs()
+        gen_fuse_history()
+        return
     ref = ref_import.load_reference()
     torch.manual_seed(0)
     if os.environ.get("GOLDEN_ONLY", "") == "f2d":
@@ -165,6 +265,7 @@ def main():
         return
     gen_forward(ref)
     gen_forward_2d(ref)
+    gen_fuse_history()
     try:
         import gen_golden_backward
         gen_golden_backward.gen_backward(ref, save)
