@@ -38,6 +38,14 @@ _SIGNATURES = {
     "fbbev_bev_pool_v2_fwd_dense_planned": (
         ctypes.c_int,
         [_p] * 7 + [_i32, _i32, _i32, _i32, _i64, _p, _p, _sz, _p]),
+    "fbbev_bev_pool_v2_sums_planned": (
+        ctypes.c_int, [_p] * 7 + [_i32, _i32, _i32, _i32, _i64, _p, _sz, _p]),
+    "fbbev_bev_pool_v2_zmean_planned": (
+        ctypes.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _sz,
+                       _p]),
+    "fbbev_bev_pool_v2_write_planned": (
+        ctypes.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _p,
+                       _sz, _p]),
     "fbbev_bev_pool_v2_bwd": (ctypes.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p]),
     "fbbev_bev_pool_v2_bwd_bczyx": (
         ctypes.c_int, [_p] * 8 + [_i32, _i32, _i64, _p, _p, _p]),

@@ -531,6 +531,61 @@ FBBEV_API int fbbev_bev_pool_v2_plan(
   return launch_status();
 }
 
+// ---- the dense op in stages (deferred materialisation, FBOCC glue) ---------
+FBBEV_API int fbbev_bev_pool_v2_sums_planned(
+    const float* depth, const float* feat, const int32_t* ranks_depth,
+    const int32_t* ranks_feat, const int32_t* ranks_bev,
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, void* plan, size_t plan_bytes,
+    fbbev_stream_t stream) {
+  int rc = dense_check(n_intervals_max, n_points, c, batch,
+                       n_voxels_per_sample, plan, plan, plan_bytes);
+  if (rc) return rc;
+  if (!use_split(c, n_voxels_per_sample)) return FBBEV_ERR_UNSUPPORTED;
+  if (n_intervals_max > 0 &&
+      (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev ||
+       !interval_starts || !interval_lengths))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  return split_launch(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                      interval_starts, interval_lengths, n_intervals_max,
+                      n_points, c, batch, n_voxels_per_sample, nullptr, plan,
+                      as_stream(stream), kSplitSums);
+}
+
+FBBEV_API int fbbev_bev_pool_v2_zmean_planned(
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, int32_t yx, float* lss_tokens, void* plan,
+    size_t plan_bytes, fbbev_stream_t stream) {
+  int rc = dense_check(n_intervals_max, n_points, c, batch,
+                       n_voxels_per_sample, lss_tokens, plan, plan_bytes);
+  if (rc) return rc;
+  if (!use_split(c, n_voxels_per_sample)) return FBBEV_ERR_UNSUPPORTED;
+  if (n_intervals_max > 0 && (!interval_starts || !interval_lengths))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  return split_zmean(interval_starts, interval_lengths, n_intervals_max,
+                     n_points, c, batch, n_voxels_per_sample, yx, lss_tokens,
+                     plan, as_stream(stream));
+}
+
+FBBEV_API int fbbev_bev_pool_v2_write_planned(
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, int32_t yx, const float* add, float* out,
+    void* plan, size_t plan_bytes, fbbev_stream_t stream) {
+  int rc = dense_check(n_intervals_max, n_points, c, batch,
+                       n_voxels_per_sample, out, plan, plan_bytes);
+  if (rc) return rc;
+  if (!use_split(c, n_voxels_per_sample)) return FBBEV_ERR_UNSUPPORTED;
+  if (n_intervals_max > 0 && (!interval_starts || !interval_lengths))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  return split_launch(nullptr, nullptr, nullptr, nullptr, nullptr,
+                      interval_starts, interval_lengths, n_intervals_max,
+                      n_points, c, batch, n_voxels_per_sample, out, plan,
+                      as_stream(stream), kSplitWrite, add, yx);
+}
+
 FBBEV_API int fbbev_bev_pool_v2_fwd_dense_planned(
     const float* depth, const float* feat, const int32_t* ranks_depth,
     const int32_t* ranks_feat, const int32_t* ranks_bev,

@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
     const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
     const int* __restrict__ interval_starts,
     const int* __restrict__ interval_lengths, int c, int zyx,
-    float* __restrict__ out) {
+    const float* __restrict__ add, int yx_n, float* __restrict__ out) {
+  // `add` (may be null): a (B, C, Y*X) map added to every Z slice while the
+  // tile streams out -- FBOCC's `bev_feat_refined[..., None] + bev_feat`
+  // (fbocc.py:365-366) without a second pass over the volume
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int pitch = c + 4;  // 16-byte aligned rows, 4-way bank spread
   float* rows = reinterpret_cast<float*>(smem_raw);  // [T + 1][pitch]
@@ -330,12 +333,21 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
   const int row0 = warp * RPW + lane / LPR;
   float* o = out + ((int64_t)b * c + row0) * zyx + v0 + 4 * g;
   const int64_t step = (int64_t)kWrWarps * RPW * zyx;
+  const float* ap = nullptr;  // this lane's four voxels in the `add` map
+  int64_t astep = 0;
+  if (add) {
+    ap = add + ((int64_t)b * c + row0) * yx_n + (v0 + 4 * g) % yx_n;
+    astep = (int64_t)kWrWarps * RPW * yx_n;
+  }
 
-  if (nrows <= 0) {  // empty tile: pure zero stream
+  if (nrows <= 0) {  // empty tile: pure zero (or `add`) stream
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (4 * g < nv)
-      for (int row = row0; row < c; row += kWrWarps * RPW, o += step)
-        st_stream(reinterpret_cast<float4*>(o), z);
+      for (int row = row0; row < c; row += kWrWarps * RPW, o += step) {
+        st_stream(reinterpret_cast<float4*>(o),
+                  ap ? __ldg(reinterpret_cast<const float4*>(ap)) : z);
+        if (ap) ap += astep;
+      }
     return;
   }
   // rows of this tile's intervals: contiguous in V, copied asynchronously,
@@ -408,8 +420,49 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
       v.y = ry[row];
       v.z = rz[row];
       v.w = rw[row];
+      if (ap) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ap));
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        ap += astep;
+      }
       st_stream(reinterpret_cast<float4*>(o), v);
     }
+  }
+}
+
+// ------------------------ Z-mean of the pooled volume ----------------------
+// lss[b][y*X + x][:] += (1/Z) * (sum of interval i) for every interval: the
+// `bev_feat.mean(-1)` FBOCC feeds to the backward projection (fbocc.py:359),
+// computed from the ~n_int interval sums instead of the dense volume (one read
+// of V instead of one read of B*C*Z*Y*X).  Token-major output (B, Y*X, C): the
+// layout the BEV queries use.  One warp per interval; an interval that spans
+// several K1 slices adds its carry rows first (as K2 does); red.global.add.v4
+// into the zero-filled map (<= Z contributions per element, order not fixed).
+__global__ void __launch_bounds__(256) zmean_kernel(
+    const float* __restrict__ V, const float* __restrict__ X,
+    const int* __restrict__ seg_rank, const int* __restrict__ interval_starts,
+    const int* __restrict__ interval_lengths, const int* __restrict__ meta,
+    int c, int zyx, int yx_n, float inv_z, float* __restrict__ lss) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= meta[0]) return;
+  const int rank = __ldg(seg_rank + i);
+  const int b = rank / zyx, yx = (rank - b * zyx) % yx_n;
+  const int st = __ldg(interval_starts + i), ln = __ldg(interval_lengths + i);
+  const int lo = st / kPtsPerWarp;
+  const int nx = (st + ln - 1) / kPtsPerWarp - lo;
+  const int c4 = c >> 2;
+  const float4* V4 = reinterpret_cast<const float4*>(V) + i * c4;
+  const float4* X4 = reinterpret_cast<const float4*>(X) + (int64_t)(lo + 1) * c4;
+  float4* dst = reinterpret_cast<float4*>(lss) + ((int64_t)b * yx_n + yx) * c4;
+  for (int v = lane; v < c4; v += kWarp) {
+    float4 a = __ldg(V4 + v);
+    for (int k = 0; k < nx; ++k) {
+      const float4 t = __ldg(X4 + (int64_t)k * c4 + v);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    a.x *= inv_z; a.y *= inv_z; a.z *= inv_z; a.w *= inv_z;
+    atomicAdd(dst + v, a);
   }
 }
 
@@ -507,8 +560,8 @@ int split_plan(const int* ranks_bev, const int* interval_starts,
 template <int T>
 static int launch_write(const SplitWs& w, const int* interval_starts,
                         const int* interval_lengths, int c, int64_t zyx,
-                        int tiles_per_b, int batch, float* out,
-                        cudaStream_t st) {
+                        int tiles_per_b, int batch, const float* add, int yx_n,
+                        float* out, cudaStream_t st) {
   const size_t smem = write_smem_bytes(T, c);
   auto k = dense_write_kernel<T>;
   if (smem > 48 * 1024) {
@@ -518,7 +571,7 @@ static int launch_write(const SplitWs& w, const int* interval_starts,
   }
   k<<<dim3((unsigned)tiles_per_b, (unsigned)batch), 2 * T, smem, st>>>(
       w.V, w.X, w.tile_first, w.seg_rank, interval_starts, interval_lengths, c,
-      (int)zyx, out);
+      (int)zyx, add, yx_n, out);
   return launch_status();
 }
 
@@ -526,13 +579,20 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
                  const int* ranks_feat, const int* ranks_bev,
                  const int* interval_starts, const int* interval_lengths,
                  int n_intervals_max, int n_points_max, int c, int batch,
-                 int64_t zyx, float* out, void* workspace, cudaStream_t st) {
-  if (reinterpret_cast<uintptr_t>(out) & 15) return FBBEV_ERR_INVALID_ARGUMENT;
+                 int64_t zyx, float* out, void* workspace, cudaStream_t st,
+                 int stages, const float* add, int yx_n) {
+  const bool do_sums = (stages & kSplitSums) != 0;
+  const bool do_write = (stages & kSplitWrite) != 0;
+  if (do_write && (reinterpret_cast<uintptr_t>(out) & 15))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (add && ((reinterpret_cast<uintptr_t>(add) & 15) || yx_n <= 0 ||
+              yx_n % 4 || zyx % yx_n))
+    return FBBEV_ERR_INVALID_ARGUMENT;
   const SplitWs w =
       split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
   const int T = split_pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
-  if (n_intervals_max > 0) {
+  if (do_sums && n_intervals_max > 0) {
     count_launch();
     const unsigned grid = (unsigned)w.n_sum_ctas;
     const int c4 = c / 4;
@@ -553,18 +613,41 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
     int rc = launch_status();
     if (rc) return rc;
   }
+  if (!do_write) return FBBEV_OK;
   count_launch();
   switch (T) {
     case 128:
       return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
-                               tiles_per_b, batch, out, st);
+                               tiles_per_b, batch, add, yx_n, out, st);
     case 64:
       return launch_write<64>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, batch, out, st);
+                              tiles_per_b, batch, add, yx_n, out, st);
     default:
       return launch_write<32>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, batch, out, st);
+                              tiles_per_b, batch, add, yx_n, out, st);
   }
+}
+
+int split_zmean(const int* interval_starts, const int* interval_lengths,
+                int n_intervals_max, int n_points_max, int c, int batch,
+                int64_t zyx, int yx_n, float* lss, void* workspace,
+                cudaStream_t st) {
+  if (yx_n <= 0 || zyx % yx_n || (reinterpret_cast<uintptr_t>(lss) & 15))
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  const SplitWs w =
+      split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
+  cudaError_t e =
+      cudaMemsetAsync(lss, 0, (size_t)batch * yx_n * c * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  if (n_intervals_max <= 0) return FBBEV_OK;
+  const float inv_z = 1.0f / (float)(zyx / yx_n);
+  const unsigned grid = (unsigned)ceil_div64((int64_t)n_intervals_max * 32, 256);
+  count_launch();
+  zmean_kernel<<<grid, 256, 0, st>>>(w.V, w.X, w.seg_rank, interval_starts,
+                                     interval_lengths, w.meta, c, (int)zyx, yx_n,
+                                     inv_z, lss);
+  return launch_status();
 }
 
 }  // namespace fbbev

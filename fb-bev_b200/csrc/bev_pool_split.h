@@ -12,11 +12,21 @@ int split_plan(const int* ranks_bev, const int* interval_starts,
                const int* interval_lengths, int n_intervals_max,
                const int* n_intervals_dev, int n_points_max, int c, int batch,
                int64_t zyx, void* workspace, cudaStream_t st);
+// stages: K1 (interval sums) and / or K2 (dense write, optionally + `add`, a
+// (B, C, yx_n) map broadcast over Z)
+constexpr int kSplitSums = 1, kSplitWrite = 2;
 int split_launch(const float* depth, const float* feat, const int* ranks_depth,
                  const int* ranks_feat, const int* ranks_bev,
                  const int* interval_starts,
                  const int* interval_lengths, int n_intervals_max,
                  int n_points_max, int c, int batch, int64_t zyx, float* out,
-                 void* workspace, cudaStream_t st);
+                 void* workspace, cudaStream_t st,
+                 int stages = kSplitSums | kSplitWrite,
+                 const float* add = nullptr, int yx_n = 0);
+// token-major Z-mean (B, yx_n, C) of the planned + summed volume
+int split_zmean(const int* interval_starts, const int* interval_lengths,
+                int n_intervals_max, int n_points_max, int c, int batch,
+                int64_t zyx, int yx_n, float* lss, void* workspace,
+                cudaStream_t st);
 
 }  // namespace fbbev

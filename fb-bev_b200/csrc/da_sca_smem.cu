@@ -35,6 +35,8 @@
 // Used when the whole map fits (n_value * E * 4 <= ~220 KB) for the head layout
 // the bank analysis holds for (8 heads x 10 channels, 1 level, 8 points, 4
 // anchors); every other shape keeps the global-memory kernel.
+#include <stdlib.h>
+
 #include "bulk.cuh"
 #include "common.cuh"
 #include "da_sca_smem.h"
@@ -42,8 +44,7 @@
 
 namespace fbbev {
 
-constexpr int kScaThreads = 512;
-constexpr int kScaWarps = kScaThreads / 32;
+constexpr int kScaMaxWarps = 24;
 constexpr int kRing = 64;          // per-warp ring of pending visible queries
 constexpr int kCH = 10, kHeads = 8, kE = 80, kZ = 4, kPts = 8;
 
@@ -246,8 +247,10 @@ __device__ __forceinline__ void sca_pass(const ScaSmemParams& P, const ScaCtx& C
   }
 }
 
+template <int kScaThreads>
 __global__ void __launch_bounds__(kScaThreads, 1) da_sca_smem_kernel(
     ScaSmemParams P) {
+  constexpr int kScaWarps = kScaThreads / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
   const int tile_bytes = P.n_value * kE * 4;
@@ -387,9 +390,9 @@ size_t da_sca_smem_workspace_bytes(int bs, int n_cams) {
 
 bool da_sca_smem_eligible(int n_cams, int n_value, int heads, int ch, int levels,
                           int points, int Z) {
-  const size_t smem = (size_t)n_value * kE * 4 + kScaWarps * kRing * 4 + 64;
+  const size_t smem = (size_t)n_value * kE * 4 + 20 * kRing * 4 + 64;
   return heads == kHeads && ch == kCH && levels == 1 && points == kPts &&
-         Z == kZ && n_cams <= 8 && smem <= 232448 - 2048;
+         Z == kZ && n_cams <= 8 && smem <= 232448 - 1024 - 768;
 }
 
 int da_sca_smem_launch(const float* value, const float* depth_prob,
@@ -419,17 +422,27 @@ int da_sca_smem_launch(const float* value, const float* depth_prob,
   da_sca_prologue_kernel<<<P.n_pairs * kCountChunks + zero_blocks, 256, 0, st>>>(
       P.mask32, bs, n_cams, nq, static_cast<int*>(workspace),
       reinterpret_cast<float4*>(out), n_out4);
-  const size_t smem = (size_t)n_value * kE * 4 + kScaWarps * kRing * 4 + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(da_sca_smem_kernel,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
-    attr_set = true;
+  // 512 or 640 threads per CTA (FBBEV_SCA_THREADS: tuning aid)
+  static int threads = 0;
+  if (threads == 0) {
+    const char* e = getenv("FBBEV_SCA_THREADS");
+    threads = (e && atoi(e) == 640) ? 640 : 512;
+    cudaFuncSetAttribute(da_sca_smem_kernel<512>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         232448 - 1024 - 768);
+    cudaFuncSetAttribute(da_sca_smem_kernel<640>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         232448 - 1024 - 768);
   }
+  const size_t smem =
+      (size_t)n_value * kE * 4 + (size_t)(threads / 32) * kRing * 4 + 64;
   // one CTA per SM; more waves when there are many (sample, camera) pairs so
   // that each pair still splits into several CTAs
   const int waves = std::max(1, (4 * P.n_pairs + n_sm - 1) / n_sm);
-  da_sca_smem_kernel<<<n_sm * waves, kScaThreads, smem, st>>>(P);
+  if (threads == 640)
+    da_sca_smem_kernel<640><<<n_sm * waves, 640, smem, st>>>(P);
+  else
+    da_sca_smem_kernel<512><<<n_sm * waves, 512, smem, st>>>(P);
   return launch_status();
 }
 

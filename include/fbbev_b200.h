@@ -119,6 +119,43 @@ int fbbev_bev_pool_v2_fwd_dense_planned(
     fbbev_stream_t stream);
 
 /*
+ * The dense op in stages, for FBOCC's glue around the two projections
+ * (mmdet3d/models/fbbev/detectors/fbocc.py:339, 357-366):
+ *     bev_feat = forward_projection(...)                       # dense volume
+ *     refined  = backward_projection(..., lss_bev=bev_feat.mean(-1), ...)
+ *     bev_feat = refined[..., None] + bev_feat                 # re-add
+ * reads the 204.8 MB volume twice and writes it twice.  After
+ * fbbev_bev_pool_v2_plan on the same workspace:
+ *   _sums_planned   runs the interval-sum stage only (V / X rows in the plan);
+ *   _zmean_planned  writes bev_feat.mean(-1) as a TOKEN-major map
+ *                   lss_tokens (B, Y*X, C) from the interval sums (the map is
+ *                   zero-filled here; red.global.add of <= Z terms per element);
+ *                   yx = Y*X;
+ *   _write_planned  materialises the (B,C,Z,Y,X) volume, adding `add` (may be
+ *                   NULL; (B, C, Y*X), e.g. the refined BEV) to every Z slice
+ *                   on the way out -- the volume is written exactly once.
+ * Requirements as for the dense op plus C % 4 == 0, (Z*Y*X) % 4 == 0, yx % 4 == 0;
+ * FBBEV_ERR_UNSUPPORTED otherwise (use the one-shot op and eager glue).
+ */
+int fbbev_bev_pool_v2_sums_planned(
+    const float* depth, const float* feat, const int32_t* ranks_depth,
+    const int32_t* ranks_feat, const int32_t* ranks_bev,
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, void* plan, size_t plan_bytes,
+    fbbev_stream_t stream);
+int fbbev_bev_pool_v2_zmean_planned(
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, int32_t yx, float* lss_tokens, void* plan,
+    size_t plan_bytes, fbbev_stream_t stream);
+int fbbev_bev_pool_v2_write_planned(
+    const int32_t* interval_starts, const int32_t* interval_lengths,
+    int32_t n_intervals_max, int32_t n_points, int32_t c, int32_t batch,
+    int64_t n_voxels_per_sample, int32_t yx, const float* add, float* out,
+    void* plan, size_t plan_bytes, fbbev_stream_t stream);
+
+/*
  * Drop-in for `bev_pool_v2_ext.bev_pool_v2_backward`
  *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:72-102 (kernel
  *   bev_pool_cuda.cu:64-118).  Intervals are runs of equal ranks_feat

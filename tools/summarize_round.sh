@@ -1,7 +1,7 @@
 # After tools/profile_round.sh: turn gpurun_out/ captures into the tracked summaries under profiles/.
-R=${1:-r01}
+R=${1:-r02}
 python tools/summarize_ncu.py launches gpurun_out/${R}_launches.csv profiles/${R}_launches.md
-for k in dense_write_kernel interval_sums_kernel linear_tf32_kernel da_sca_fwd_kernel; do
+for k in dense_write_kernel interval_sums_kernel linear_tf32_kernel da_sca_smem_kernel msda_fused_fwd_kernel history_warp_kernel; do
   [ -f gpurun_out/${R}_$k.ncu-rep ] && python tools/summarize_ncu.py kernel gpurun_out/${R}_$k.ncu-rep profiles/${R}_$k.json
 done
 python - <<PY
