@@ -877,6 +877,13 @@ def main():
         except Exception as ex:
             extra["reference_cuda"] = {"unavailable": str(ex)[:160]}
 
+    # ---- the detector's glue around the two calls (fbocc.py:339, 357-366) ----
+    if world == 1 and args.config == "fbocc200" and not args.no_reference_cuda:
+        try:
+            extra["pipeline_readd"] = time_pipeline_readd(w, flush)
+        except Exception as ex:
+            extra["pipeline_readd"] = {"unavailable": str(ex)[:160]}
+
     # ---- next stage: the history warp ----------------
     if world == 1 and args.config == "fbocc200" and not args.no_reference_cuda:
         try:
@@ -974,6 +981,59 @@ def frames16_block(world, rank, dev, flush, barrier, steps):
                          "BackwardProjection.forward(out=slot) wrote into")
     del w16
     torch.cuda.empty_cache()
+    return res
+
+
+def time_pipeline_readd(w, flush):
+    """forward -> mean(-1) -> backward -> refined[..., None] + bev_feat, the
+    three lines of FBOCC.extract_img_bev_feat around the plugin calls: the
+    literal sequence (plugin calls + two torch ops over the 204.8 MB volume)
+    against forward_backward_readd (interval sums -> Z-mean -> backward ->
+    dense write with the re-add: the volume is written once).  CUDA-graph
+    replays of each, L2 flushed, device clock."""
+    from fbbev_b200.view_transformation.forward_projection import \
+        forward_backward_readd
+
+    @torch.no_grad()
+    def literal():
+        bev = w.vt(w.cam, w.feat, w.depth)
+        ref = w.bp([w.feat], None, lss_bev=bev.mean(-1), cam_params=w.cam,
+                   pred_img_depth=w.depth)
+        return ref[..., None] + bev
+
+    @torch.no_grad()
+    def fused():
+        return forward_backward_readd(w.vt, w.bp, w.cam, w.feat, w.depth)[0]
+
+    res = {}
+    for name, fn in (("literal_ms", literal), ("fused_ms", fused)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        for _ in range(3):
+            g.replay()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            s = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        res[name] = statistics.median(ts)
+        del g, out
+    res["speedup"] = res["literal_ms"] / res["fused_ms"]
+    res["what"] = ("F + bev_feat.mean(-1) + B + refined[..., None] + bev_feat "
+                   "(fbocc.py:339, 357-366), one frame, graph replay")
     return res
 
 

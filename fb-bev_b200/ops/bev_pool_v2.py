@@ -17,7 +17,8 @@ import torch
 
 from .. import _lib
 
-__all__ = ['bev_pool_v2', 'bev_pool_v2_dense', 'QuickCumsumCuda',
+__all__ = ['DeferredVolume', 'bev_pool_v2_deferred',
+           'bev_pool_v2', 'bev_pool_v2_dense', 'QuickCumsumCuda',
            'voxel_pooling_prepare_v2', 'voxel_pooling_prepare_from_cams',
            'VoxelIndex']
 
@@ -213,6 +214,102 @@ def bev_pool_v2_dense(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     return _BevPoolV2Dense.apply(depth, feat, ranks_depth, ranks_feat,
                                  ranks_bev, bev_feat_shape, interval_starts,
                                  interval_lengths, n_intervals_dev, n_kept_dev)
+
+
+class DeferredVolume:
+    """The pooled volume held as interval sums, materialised on demand.
+
+    FBOCC's glue around the two projections (fbocc.py:339, 357-366)
+
+        bev_feat = forward_projection(...)
+        refined  = backward_projection(..., lss_bev=bev_feat.mean(-1), ...)
+        bev_feat = refined[..., None] + bev_feat
+
+    reads the dense volume twice and writes it twice (820 MB for 200x200x16 x
+    80).  Here the forward projection stops after the interval-sum stage;
+    :meth:`mean_z` produces ``bev_feat.mean(-1)`` from the ~n_int interval sums
+    and :meth:`materialize` writes the volume ONCE, adding the refined BEV to
+    every Z slice on the way out.  Inference only (no autograd)."""
+
+    def __init__(self, shape, idx, ws, ws_bytes, n_int_cap, n_points):
+        self.shape = shape            # (B, Z, Y, X, C)
+        self._idx, self._ws, self._ws_bytes = idx, ws, ws_bytes
+        self._cap, self._n_points = n_int_cap, n_points
+
+    def mean_z(self):
+        """``volume.mean(-1)`` of the (B, C, Y, X, Z) view: (B, C, Y, X), a
+        channels-last-strided view of a token-major (B, Y*X, C) buffer (the
+        layout BackwardProjection's BEV queries use)."""
+        B, Z, Y, X, C = self.shape
+        st, ln = self._idx
+        dev = self._ws.device
+        lss = torch.empty((B, Y * X, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fbbev_bev_pool_v2_zmean_planned(
+                _lib.ptr(st), _lib.ptr(ln), self._cap, self._n_points, C, B,
+                Z * Y * X, Y * X, _lib.ptr(lss), _lib.ptr(self._ws),
+                self._ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(rc, 'fbbev_bev_pool_v2_zmean_planned')
+        return lss.view(B, Y, X, C).permute(0, 3, 1, 2)
+
+    def materialize(self, add=None):
+        """The contiguous (B, C, Z, Y, X) volume, plus ``add[..., None]``
+        ((B, C, Y, X), e.g. the refined BEV) broadcast over Z when given."""
+        B, Z, Y, X, C = self.shape
+        st, ln = self._idx
+        dev = self._ws.device
+        out = torch.empty((B, C, Z, Y, X), dtype=torch.float32, device=dev)
+        if add is not None:
+            _lib.require_cuda(add)
+            assert tuple(add.shape) == (B, C, Y, X), add.shape
+            add = add.contiguous().float()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fbbev_bev_pool_v2_write_planned(
+                _lib.ptr(st), _lib.ptr(ln), self._cap, self._n_points, C, B,
+                Z * Y * X, Y * X, _lib.ptr(add), _lib.ptr(out),
+                _lib.ptr(self._ws), self._ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(rc, 'fbbev_bev_pool_v2_write_planned')
+        return out
+
+
+def deferred_supported(bev_feat_shape):
+    B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
+    return (C % 4 == 0 and C <= 512 and (Z * Y * X) % 4 == 0 and
+            (Y * X) % 4 == 0 and B * Z * Y * X <= 2 ** 31 - 1)
+
+
+def bev_pool_v2_deferred(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                         bev_feat_shape, interval_starts, interval_lengths,
+                         n_intervals_dev=None):
+    """Plan + interval sums of the dense op; returns a :class:`DeferredVolume`
+    (``fbbev_bev_pool_v2_plan`` + ``fbbev_bev_pool_v2_sums_planned``)."""
+    dev = _lib.require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                            interval_starts, interval_lengths, n_intervals_dev)
+    B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
+    assert feat.shape[-1] == C and deferred_supported(bev_feat_shape)
+    depth = depth.contiguous().float()
+    feat = feat.contiguous().float()
+    rb, rd, rf = (t.contiguous().int() for t in
+                  (ranks_bev, ranks_depth, ranks_feat))
+    st, ln = interval_starts.contiguous().int(), interval_lengths.contiguous().int()
+    L = _lib.lib()
+    n_points = rb.shape[0]
+    cap = min(ln.shape[0], B * Z * Y * X)
+    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, Z * Y * X, cap,
+                                                         n_points, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        sp = _lib.stream_ptr(dev)
+        _lib.check(L.fbbev_bev_pool_v2_plan(
+            _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), cap,
+            _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X, _lib.ptr(ws),
+            ws_bytes, sp), 'fbbev_bev_pool_v2_plan')
+        _lib.check(L.fbbev_bev_pool_v2_sums_planned(
+            _lib.ptr(depth), _lib.ptr(feat), _lib.ptr(rd), _lib.ptr(rf),
+            _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), cap, n_points, C, B,
+            Z * Y * X, _lib.ptr(ws), ws_bytes, sp),
+            'fbbev_bev_pool_v2_sums_planned')
+    return DeferredVolume((B, Z, Y, X, C), (st, ln), ws, ws_bytes, cap, n_points)
 
 
 def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,

@@ -259,10 +259,15 @@ def bev_query_init(embedding, lss_bev):
     (bs, nq, E)-contiguous buffer."""
     dev = _lib.require_cuda(embedding, lss_bev)
     emb = embedding.detach().contiguous().float()
-    lss = lss_bev.contiguous().float()
-    bs, E = lss.shape[:2]
+    bs, E = lss_bev.shape[:2]
     nq = emb.shape[0]
-    assert emb.shape[1] == E and lss[0, 0].numel() == nq
+    assert emb.shape[1] == E and lss_bev[0, 0].numel() == nq
+    if lss_bev.dim() == 4 and lss_bev.stride(1) == 1 and \
+            lss_bev.permute(0, 2, 3, 1).is_contiguous():
+        # token-major already (e.g. DeferredVolume.mean_z()): a plain add
+        tok = lss_bev.permute(0, 2, 3, 1).reshape(bs, nq, E).float()
+        return (emb.unsqueeze(0) + tok).permute(1, 0, 2)
+    lss = lss_bev.contiguous().float()
     out = torch.empty((bs, nq, E), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.lib().fbbev_bev_query_init(

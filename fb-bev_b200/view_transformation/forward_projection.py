@@ -28,13 +28,14 @@ import torch.nn as nn
 
 import os
 
-from ..ops.bev_pool_v2 import (VoxelIndex, bev_pool_v2, bev_pool_v2_dense,
+from ..ops.bev_pool_v2 import (VoxelIndex, bev_pool_v2, bev_pool_v2_deferred,
+                               bev_pool_v2_dense, deferred_supported,
                                voxel_pooling_prepare_from_cams,
                                voxel_pooling_prepare_v2)
 from ..registry import BaseModule, register
 
 __all__ = ['gen_dx_bx', 'LSSViewTransformerFunction3D',
-           'LSSViewTransformerFunction']
+           'LSSViewTransformerFunction', 'forward_backward_readd']
 
 
 def inv3x3_many(*mats):
@@ -271,6 +272,32 @@ class LSSViewTransformerFunction3D(_LSSBase):
             self.pre_compute(cam_params)
         return self.view_transform_core(cam_params, depth, tran_feat)
 
+    def forward_deferred(self, cam_params, context, depth):
+        """Index + interval sums only: a :class:`~..ops.bev_pool_v2.
+        DeferredVolume` whose ``mean_z()`` is ``forward(...).mean(-1)`` and
+        whose ``materialize(add)`` is ``forward(...)`` (+ ``add[..., None]``)
+        in the contiguous (B, C, Z, Y, X) layout -- see
+        :func:`forward_backward_readd`.  Returns None when the shape is not
+        covered (caller falls back to ``forward``)."""
+        feat = context.permute(0, 1, 3, 4, 2)
+        shape = self._bev_feat_shape(depth, feat)
+        if torch.is_grad_enabled() and (context.requires_grad or
+                                        depth.requires_grad):
+            return None
+        if not deferred_supported(shape) or not depth.is_cuda:
+            return None
+        if self.accelerate:
+            self.pre_compute(cam_params)
+            idx = self._index
+        elif self.fused_geometry:
+            idx = self.prepare_index_from_cams(*cam_params)
+        else:
+            idx = self.prepare_index(self.get_lidar_coor(*cam_params))
+        return bev_pool_v2_deferred(
+            depth, feat, idx.ranks_depth, idx.ranks_feat, idx.ranks_bev, shape,
+            idx.interval_starts, idx.interval_lengths,
+            n_intervals_dev=idx.n_intervals_dev)
+
     # -- view_transformer.py:646-660 ------------------------------------
     def forward(self, cam_params, context, depth, **kwargs):
         """cam_params = (rots, trans, intrins, post_rots, post_trans, bda);
@@ -318,3 +345,39 @@ class LSSViewTransformerFunction(_LSSBase):
 
     def forward(self, cam_params, context, depth, **kwargs):
         return self.view_transform(cam_params, depth, context)
+
+
+def forward_backward_readd(forward_projection, backward_projection, cam_params,
+                           context, depth, img_metas=None, readd=True,
+                           bev_mask=None):
+    """The three lines of ``FBOCC.extract_img_bev_feat`` around the two
+    projections (fbocc.py:339, 357-366)::
+
+        bev_feat = forward_projection(cam_params, context, depth)
+        refined  = backward_projection([context], img_metas,
+                                       lss_bev=bev_feat.mean(-1), ...)
+        bev_feat = refined[..., None] + bev_feat     # if self.readd
+
+    with the dense volume written once instead of written, read twice and
+    written again: ``mean(-1)`` comes from the interval sums
+    (``fbbev_bev_pool_v2_zmean_planned``) and the re-add rides on the dense
+    write (``fbbev_bev_pool_v2_write_planned``).  Returns ``(bev_feat (B, C, Y,
+    X, Z), refined (B, C, Y, X))``; falls back to the literal sequence when the
+    deferred path does not cover the call (training, odd shapes)."""
+    dv = None
+    if isinstance(forward_projection, LSSViewTransformerFunction3D) and \
+            not forward_projection.extra_relu:
+        dv = forward_projection.forward_deferred(cam_params, context, depth)
+    if dv is None:
+        bev_feat = forward_projection(cam_params, context, depth)
+        refined = backward_projection(
+            [context], img_metas, lss_bev=bev_feat.mean(-1),
+            cam_params=cam_params, bev_mask=bev_mask, gt_bboxes_3d=None,
+            pred_img_depth=depth)
+        return (refined[..., None] + bev_feat if readd else refined), refined
+    refined = backward_projection(
+        [context], img_metas, lss_bev=dv.mean_z(), cam_params=cam_params,
+        bev_mask=bev_mask, gt_bboxes_3d=None, pred_img_depth=depth)
+    if not readd:
+        return refined, refined
+    return dv.materialize(add=refined).permute(0, 1, 3, 4, 2), refined

@@ -456,3 +456,42 @@ def test_bev_query_init_kernel(bs, hw, E):
     assert got.shape == want.shape == (nq, bs, E)
     assert torch.equal(got, want)
     assert got.permute(1, 0, 2).is_contiguous()
+
+
+@pytest.mark.parametrize("B,bev,grid,inp", [
+    (1, (200, 200), "fbocc_200", (256, 704)),     # the bench workload
+    (2, (100, 100), "fbocc_shipped", (256, 704)),  # shipped FB-OCC grid, 2 frames
+])
+def test_forward_backward_readd_glue(B, bev, grid, inp):
+    """FBOCC.extract_img_bev_feat's three lines around the projections
+    (fbocc.py:339, 357-366) with the volume written once: mean(-1) from the
+    interval sums, the re-add fused into the dense write == the literal
+    sequence forward -> mean(-1) -> backward -> refined[..., None] + bev."""
+    from fbbev_b200 import synthetic
+    from fbbev_b200.view_transformation.forward_projection import (
+        LSSViewTransformerFunction3D, forward_backward_readd)
+    vt = LSSViewTransformerFunction3D(synthetic.GRID_CONFIGS[grid], inp, 16)
+    H, W = inp[0] // 16, inp[1] // 16
+    bp = _bp_module(bev, 80, [(H, W)], inp, B,
+                    z_step=1.6, dbound=(2.0, 42.0, 0.5))
+    cams = synthetic.make_cam_params(B, 6, inp, device=DEV, jitter=1.0)
+    depth, feat = synthetic.make_depth_feat(B, 6, vt.D, H, W, 80, device=DEV)
+    with torch.no_grad():
+        bev_feat = vt(cams, feat, depth)                       # (B,C,Y,X,Z)
+        lss = bev_feat.mean(-1)
+        refined = bp([feat], None, lss_bev=lss, cam_params=cams,
+                     pred_img_depth=depth)
+        want = refined[..., None] + bev_feat
+        dv = vt.forward_deferred(cams, feat, depth)
+        assert dv is not None
+        np.testing.assert_allclose(dv.mean_z().cpu().numpy(), lss.cpu().numpy(),
+                                   rtol=0, atol=1e-5)
+        assert torch.equal(dv.materialize().permute(0, 1, 3, 4, 2), bev_feat)
+        got, refined2 = forward_backward_readd(vt, bp, cams, feat, depth)
+        got_noadd, _ = forward_backward_readd(vt, bp, cams, feat, depth,
+                                              readd=False)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(refined2.cpu().numpy(), refined.cpu().numpy(),
+                               rtol=0, atol=ATOL)
+    assert float((got - want).abs().max()) <= ATOL
+    assert torch.equal(got_noadd, refined2)
