@@ -45,7 +45,9 @@
 namespace fbbev {
 
 constexpr int kScaMaxWarps = 24;
-constexpr int kRing = 64;          // per-warp ring of pending visible queries
+constexpr int kRoundBatches = 64;   // 32-query batches scanned per round
+constexpr int kListCap = kRoundBatches * 32;   // visible-query codes (uint16)
+constexpr int kListBytes = kListCap * 2;
 constexpr int kCH = 10, kHeads = 8, kE = 80, kZ = 4, kPts = 8;
 
 struct ScaSmemParams {
@@ -254,11 +256,11 @@ __global__ void __launch_bounds__(kScaThreads, 1) da_sca_smem_kernel(
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
   const int tile_bytes = P.n_value * kE * 4;
-  int* ring = reinterpret_cast<int*>(smem_raw + tile_bytes);  // [warps][kRing]
+  unsigned char* ring = smem_raw + tile_bytes;               // the CTA's list
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + tile_bytes +
-                                              kScaWarps * kRing * 4);
+                                              kListBytes);
   __shared__ int s_pair, s_k, s_K, s_next, s_left_n;
-  __shared__ int s_left[kScaWarps * 4];
+  __shared__ int s_left[4];
   __shared__ int s_cnt[64];   // per-pair counts (chunked when n_pairs > 64)
   __shared__ long long s_total;
 
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kScaThreads, 1) da_sca_smem_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = lane >> 3;
-  int* wq = ring + warp * kRing;
+  uint16_t* list = reinterpret_cast<uint16_t*>(ring);   // [kListCap] codes
   const uint32_t* mask_pair = P.mask32 + ((int64_t)n * P.bs + b) * P.nq;
   ScaCtx C;
   C.tile = tile;
@@ -347,37 +349,46 @@ __global__ void __launch_bounds__(kScaThreads, 1) da_sca_smem_kernel(
   const int n_batches = (P.nq + 31) / 32;
   const int k = s_k, K = s_K;
   bool tile_ready = false;
-  int head = 0, tail = 0;                    // ring indices (warp-uniform)
 
   // CTA k of the pair owns the 32-query batches j = k (mod K) -- interleaved,
-  // so every CTA samples the camera's visible wedge evenly -- and its warps
-  // pull them from a shared counter (batches differ 0..32 in visible queries)
-  for (;;) {
-    int jl = 0;
-    if (lane == 0) jl = atomicAdd(&s_next, 1);
-    jl = __shfl_sync(kFull, jl, 0);
-    const int j = k + jl * K;
-    if (j >= n_batches) break;
-    const int q = j * 32 + lane;
-    const bool seen = q < P.nq && __ldg(mask_pair + q) != 0;        // (:165)
-    const unsigned bal = __ballot_sync(kFull, seen);
-    if (seen) wq[(tail + __popc(bal & ((1u << lane) - 1))) & (kRing - 1)] = q;
-    tail += __popc(bal);
-    __syncwarp();
-    while (tail - head >= 4) {
-      const int qq = wq[(head + slot) & (kRing - 1)];
-      head += 4;
-      sca_pass(P, C, qq, true, lane, tile_ready);
+  // so every CTA samples the camera's visible wedge evenly.  Per round of up
+  // to kRoundBatches batches: (A) the warps scan the batches and compact the
+  // visible queries into ONE list for the CTA (16-bit codes: batch-in-round,
+  // lane); (B) the warps pull groups of four queries from that list through a
+  // shared counter.  The unit of scheduling is a pass, so the tail of a CTA is
+  // at most one pass per warp (a whole batch of up to eight passes before:
+  // 28 % of the warp time was spent waiting at the final barrier).
+  for (int round = 0; k + (int64_t)round * K < n_batches;
+       round += kRoundBatches) {
+    if (threadIdx.x == 0) { s_next = 0; s_left_n = 0; }
+    __syncthreads();
+    for (int jl = warp; jl < kRoundBatches; jl += kScaWarps) {
+      const int64_t j = k + (int64_t)(round + jl) * K;
+      if (j >= n_batches) break;
+      const int q = (int)j * 32 + lane;
+      const bool seen = q < P.nq && __ldg(mask_pair + q) != 0;      // (:165)
+      const unsigned bal = __ballot_sync(kFull, seen);
+      int base = 0;
+      if (lane == 0 && bal) base = atomicAdd(&s_left_n, __popc(bal));
+      base = __shfl_sync(kFull, base, 0);
+      if (seen)
+        list[base + __popc(bal & ((1u << lane) - 1))] =
+            (uint16_t)((jl << 5) | lane);
     }
-  }
-  // leftovers (< 4 per warp) are pooled so that they still run four at a time
-  if (lane < tail - head)
-    s_left[atomicAdd(&s_left_n, 1)] = wq[(head + lane) & (kRing - 1)];
-  __syncthreads();
-  const int n_left = s_left_n;
-  for (int g = warp; g * 4 < n_left; g += kScaWarps) {
-    const bool active = g * 4 + slot < n_left;
-    sca_pass(P, C, active ? s_left[g * 4 + slot] : 0, active, lane, tile_ready);
+    __syncthreads();
+    const int n_vis = s_left_n;
+    for (;;) {
+      int p0 = 0;
+      if (lane == 0) p0 = atomicAdd(&s_next, 4);
+      p0 = __shfl_sync(kFull, p0, 0);
+      if (p0 >= n_vis) break;
+      const bool active = p0 + slot < n_vis;
+      const int code = active ? (int)list[p0 + slot] : 0;
+      const int q = (int)((k + (int64_t)(round + (code >> 5)) * K) * 32) +
+                    (code & 31);
+      sca_pass(P, C, q, active, lane, tile_ready);
+    }
+    __syncthreads();   // the list is rewritten by the next round
   }
   // the bulk copies must have landed before the CTA (and its shared memory)
   // goes away, also when this warp never touched the tile
@@ -390,7 +401,7 @@ size_t da_sca_smem_workspace_bytes(int bs, int n_cams) {
 
 bool da_sca_smem_eligible(int n_cams, int n_value, int heads, int ch, int levels,
                           int points, int Z) {
-  const size_t smem = (size_t)n_value * kE * 4 + 20 * kRing * 4 + 64;
+  const size_t smem = (size_t)n_value * kE * 4 + kListBytes + 64;
   return heads == kHeads && ch == kCH && levels == 1 && points == kPts &&
          Z == kZ && n_cams <= 8 && smem <= 232448 - 1024 - 768;
 }
@@ -434,8 +445,7 @@ int da_sca_smem_launch(const float* value, const float* depth_prob,
                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                          232448 - 1024 - 768);
   }
-  const size_t smem =
-      (size_t)n_value * kE * 4 + (size_t)(threads / 32) * kRing * 4 + 64;
+  const size_t smem = (size_t)n_value * kE * 4 + kListBytes + 64;
   // one CTA per SM; more waves when there are many (sample, camera) pairs so
   // that each pair still splits into several CTAs
   const int waves = std::max(1, (4 * P.n_pairs + n_sm - 1) / n_sm);

@@ -102,6 +102,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src,
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// shared -> global bulk store (TMA, 1-D): `bytes` a multiple of 16, both
+// addresses 16-byte aligned; tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {  // smem sources reusable
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() {       // stores complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
@@ -436,7 +452,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       const uint32_t taddr =
           tmem_base + ((uint32_t)(q * 32) << 16) + grp * (uint32_t)npad;
       if (LN) {
-        group_sync();  // the previous tile's rows have left the slab
+        bulk_wait_read0();  // this thread's row of the previous tile has left
+        group_sync();       // ... and so have all the others
         if (p.residual) {
 #pragma unroll 1
           for (int c = 0; c < nc16; ++c) {
@@ -464,8 +481,10 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           asm volatile("cp.async.wait_group 0;" ::: "memory");
           group_sync();
         }
-        // pass 1: accumulator + bias (+ ReLU) + residual -> my slab row, sum
-        float sum = 0.f;
+        // pass 1: accumulator + bias (+ ReLU) + residual -> my slab row; sum and
+        // sum of squares about a shift K = the row's first element (a one-pass
+        // variance that does not cancel: |mean - K| is a few sigma at most)
+        float sum = 0.f, sq = 0.f, shiftK = 0.f;
 #pragma unroll 1
         for (int c = 0; c < nc16; ++c) {
           float v[16];
@@ -492,22 +511,21 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                 t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
               }
               *cell = t;
-              sum += (t.x + t.y) + (t.z + t.w);
+              if (col == 0) shiftK = t.x;
+              const float a = t.x - shiftK, b = t.y - shiftK, cc = t.z - shiftK,
+                          d = t.w - shiftK;
+              sum += (a + b) + (cc + d);
+              sq += (a * a + b * b) + (cc * cc + d * d);
             }
           }
         }
         if (gt == 0) TRACE(3 + grp, 800 + tc);
-        // pass 2 / 3: variance about the mean, normalise in place
+        // pass 2: normalise in place
         const int c4 = N >> 2;
-        const float mean = sum / (float)N;
-        float var = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < c4; ++j) {
-          const float4 t = *reinterpret_cast<const float4*>(my_row + 4 * j);
-          const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
-          var += (a * a + b * b) + (c * c + d * d);
-        }
-        const float rstd = rsqrtf(var / (float)N + p.eps);
+        const float dm = sum / (float)N;       // mean - K
+        const float mean = shiftK + dm;
+        const float var = fmaxf(sq / (float)N - dm * dm, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
         const float4* g4 = reinterpret_cast<const float4*>(s_gamma);
         const float4* b4 = reinterpret_cast<const float4*>(s_beta);
 #pragma unroll 4
@@ -520,30 +538,16 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                               fmaf((t.w - mean) * rstd, g.w, b.w));
         }
         if (gt == 0) TRACE(3 + grp, 900 + tc);
-        group_sync();
-        // whole rows slab -> global: consecutive lanes, consecutive 16 bytes
-        {
-          int r = gt / c4, ch = gt - r * c4;
-          const int dq = 128 / c4, dr = 128 - dq * c4;
-#pragma unroll 1
-          while (r < kTileM) {
-            float4 t[4];
-            int rr[4], cc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              rr[u] = r; cc[u] = ch;
-              if (r < kTileM)
-                t[u] = *reinterpret_cast<const float4*>(slab + (size_t)r * pitch + 4 * ch);
-              r += dq; ch += dr;
-              if (ch >= c4) { ch -= c4; ++r; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (rr[u] < kTileM && row0 + rr[u] < row_end)
-                *reinterpret_cast<float4*>(
-                    p.y + (size_t)(row0 + rr[u]) * p.ldy + 4 * cc[u]) = t[u];
-          }
+        // the finished row leaves as ONE bulk (TMA) store issued by its own
+        // thread: N * 4 contiguous bytes in the slab and in y.  No barrier and
+        // no LDS / STG loop: the thread's own STS are ordered before its bulk
+        // copy by the proxy fence.
+        if (row0 + gt < row_end) {
+          fence_proxy_async();
+          bulk_s2g(p.y + (size_t)(row0 + gt) * p.ldy, smem_u32(my_row),
+                   (uint32_t)N * 4u);
         }
+        bulk_commit();
         if (gt == 0) TRACE(3 + grp, 1000 + tc);
       } else {
         mbar_wait(bar_tfull + 8u * grp, aph);
@@ -606,6 +610,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     }
   }
 
+  if (LN) bulk_wait0();  // every row's bulk store has completed
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TRACE(0, 2);
