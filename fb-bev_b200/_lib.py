@@ -58,6 +58,7 @@ _SIGNATURES = {
         ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32] * 3 +
         [ctypes.c_float] * 4 + [_p] * 4),
     "fbbev_bev_query_init": (ctypes.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "fbbev_tokens_to_map": (ctypes.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "fbbev_msda_fwd": (ctypes.c_int, [_p] * 5 + [_i32] * 7 + [_p, _p]),
     "fbbev_msda_bwd": (ctypes.c_int, [_p] * 6 + [_i32] * 7 + [_p] * 4),
     "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 8 + [_p, _p]),

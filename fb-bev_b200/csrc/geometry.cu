@@ -143,9 +143,56 @@ __global__ void __launch_bounds__(256) bev_query_init_v4_kernel(
   }
 }
 
+// out[b, e, q] = in[b, q, e]: the (bs, nq, E) token tensor the encoder ends with
+// -> the (bs, E, bev_h, bev_w) map BackwardProjection returns
+// (backward_projection.py:131-133: permute(0, 2, 1).view(...).contiguous()).
+// 128 queries x 32 channels per block through shared memory, 128-bit accesses on
+// both sides.
+__global__ void __launch_bounds__(256) tokens_to_map_kernel(
+    const float* __restrict__ in, int bs, int nq, int E, float* __restrict__ out) {
+  __shared__ __align__(16) float tile[32][132];
+  const int q0 = blockIdx.x * 128, e0 = blockIdx.y * 32, b = blockIdx.z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int ql = idx >> 3, e4 = idx & 7;
+    const int q = q0 + ql, e = e0 + 4 * e4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq && e < E)
+      v = __ldg(reinterpret_cast<const float4*>(in + ((int64_t)b * nq + q) * E + e));
+    tile[4 * e4 + 0][ql] = v.x;
+    tile[4 * e4 + 1][ql] = v.y;
+    tile[4 * e4 + 2][ql] = v.z;
+    tile[4 * e4 + 3][ql] = v.w;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = e0 + ty + 8 * i, q = q0 + 4 * lane;
+    if (e < E && q < nq)
+      st_stream(reinterpret_cast<float4*>(out + ((int64_t)b * E + e) * nq + q),
+                *reinterpret_cast<const float4*>(&tile[ty + 8 * i][4 * lane]));
+  }
+}
+
 }  // namespace fbbev
 
 using namespace fbbev;
+
+FBBEV_API int fbbev_tokens_to_map(const float* tokens, int32_t bs, int32_t nq,
+                                  int32_t E, float* out, fbbev_stream_t stream) {
+  if (bs <= 0 || nq <= 0 || E <= 0 || !tokens || !out)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (nq % 4 || E % 4 || bs > 65535 || (E + 31) / 32 > 65535 ||
+      ((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return FBBEV_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)((nq + 127) / 128), (unsigned)((E + 31) / 32),
+                  (unsigned)bs);
+  count_launch();
+  tokens_to_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(tokens, bs, nq, E, out);
+  return launch_status();
+}
 
 FBBEV_API int fbbev_bev_query_init(const float* embedding, const float* lss_bev,
                                    int32_t bs, int32_t nq, int32_t E, float* out,

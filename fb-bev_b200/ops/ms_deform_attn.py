@@ -22,7 +22,7 @@ __all__ = ['MultiScaleDeformableAttnFunction_fp32',
            'ms_deform_attn_fused', 'ms_deform_attn_unfused',
            'da_spatial_cross_attention_core',
            'da_spatial_cross_attention_core_autograd', 'point_sampling',
-           'bev_query_init',
+           'bev_query_init', 'tokens_to_map',
            'needs_grad']
 
 
@@ -275,6 +275,28 @@ def bev_query_init(embedding, lss_bev):
             _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_bev_query_init')
     return out.permute(1, 0, 2)
+
+
+def tokens_to_map(tokens, bev_h, bev_w, out=None):
+    """``tokens.permute(0, 2, 1).view(bs, E, bev_h, bev_w).contiguous()``
+    (backward_projection.py:131-133) as one transposing kernel
+    (``fbbev_tokens_to_map``); ``out``: optional destination (e.g. a gather
+    slot).  Returns None when the shape is not covered (caller falls back)."""
+    bs, nq, E = tokens.shape
+    if not tokens.is_cuda or tokens.dtype != torch.float32 or nq % 4 or E % 4 \
+            or not tokens.is_contiguous():
+        return None
+    if out is None:
+        out = torch.empty((bs, E, bev_h, bev_w), dtype=torch.float32,
+                          device=tokens.device)
+    elif not out.is_contiguous() or tuple(out.shape) != (bs, E, bev_h, bev_w):
+        return None
+    with torch.cuda.device(tokens.device):
+        rc = _lib.lib().fbbev_tokens_to_map(
+            _lib.ptr(tokens), bs, nq, E, _lib.ptr(out),
+            _lib.stream_ptr(tokens.device))
+    _lib.check(rc, 'fbbev_tokens_to_map')
+    return out
 
 
 def point_sampling(axes, inv_bda, trans, ego2cam, post_rots, post_trans,

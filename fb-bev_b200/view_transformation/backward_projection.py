@@ -1149,6 +1149,12 @@ class BackwardProjection(BaseModule):
             bev_pos=bev_pos, img_metas=img_metas, cam_params=cam_params,
             gt_bboxes_3d=gt_bboxes_3d, pred_img_depth=pred_img_depth,
             prev_bev=None, bev_mask=bev_mask)
+        if bev.dim() == 3 and not needs_grad(bev):
+            # (bs, nq, E) -> (bs, E, h, w) as one transposing kernel
+            res = _msda_ops.tokens_to_map(bev, self.bev_h, self.bev_w, out=out) \
+                if bev.is_cuda else None
+            if res is not None:
+                return res
         bev = bev.permute(0, 2, 1).view(bs, -1, self.bev_h, self.bev_w)
         if out is not None:
             return out.copy_(bev)

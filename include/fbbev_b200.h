@@ -278,6 +278,15 @@ int fbbev_bev_query_init(const float* embedding, const float* lss_bev,
                          fbbev_stream_t stream);
 
 /*
+ * out[b, e, q] = tokens[b, q, e]: the last line of `BackwardProjection.forward`
+ *   (backward_projection.py:131-133: bev.permute(0, 2, 1).view(bs, -1, bev_h,
+ *   bev_w).contiguous()).  tokens (bs, nq, E), out (bs, E, nq), both dense fp32,
+ *   16-byte aligned; nq % 4 == 0 and E % 4 == 0, else FBBEV_ERR_UNSUPPORTED.
+ */
+int fbbev_tokens_to_map(const float* tokens, int32_t bs, int32_t nq, int32_t E,
+                        float* out, fbbev_stream_t stream);
+
+/*
  * Drop-in for `ext_module.ms_deform_attn_forward` (mmcv-full 1.5.2 `_ext`)
  *   call site: .../backward_projection/bevformer_utils/
  *   multi_scale_deformable_attn_function.py:127-133.

@@ -441,7 +441,8 @@ def test_da_sca_smem_kernel_vs_global_kernel_and_oracle(bs, nq, hw):
 
 
 @pytest.mark.parametrize("bs,hw,E", [(1, (200, 200), 80), (3, (13, 7), 64),
-                                     (2, (5, 33), 20)])
+                                     (2, (5, 33), 20), (2, (6, 22), 20),
+                                     (3, (10, 14), 64)])
 def test_bev_query_init_kernel(bs, hw, E):
     """fbbev_bev_query_init == embedding.unsqueeze(1).repeat(1, bs, 1) +
     lss_bev.flatten(2).permute(2, 0, 1) (backward_projection.py:93-97), bit for
@@ -456,6 +457,17 @@ def test_bev_query_init_kernel(bs, hw, E):
     assert got.shape == want.shape == (nq, bs, E)
     assert torch.equal(got, want)
     assert got.permute(1, 0, 2).is_contiguous()
+    # and the way back: (bs, nq, E) tokens -> (bs, E, h, w) map
+    from fbbev_b200.ops.ms_deform_attn import tokens_to_map
+    tok = got.permute(1, 0, 2).contiguous()
+    back = tokens_to_map(tok, *hw)
+    ref = tok.permute(0, 2, 1).reshape(bs, E, *hw)
+    if nq % 4 == 0 and E % 4 == 0:
+        assert back is not None and torch.equal(back, ref)
+        slot = torch.empty(ref.shape, device=DEV)
+        assert tokens_to_map(tok, *hw, out=slot) is slot and torch.equal(slot, ref)
+    else:
+        assert back is None
 
 
 @pytest.mark.parametrize("B,bev,grid,inp", [
