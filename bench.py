@@ -1094,7 +1094,7 @@ def time_reference_gpu(w, idx, flush, our_step_ms):
     restatement of everything else (oracle/gpu_ref.py)."""
     from oracle import gpu_ref, ref_cuda
 
-    def wall(fn, iters=5, warm=2):
+    def wall(fn, iters=7, warm=4):
         for _ in range(warm):
             fn()
         ts = []
@@ -1107,9 +1107,9 @@ def time_reference_gpu(w, idx, flush, our_step_ms):
             ts.append(time.perf_counter() - t0)
         return statistics.median(ts) * 1e6
 
-    out = {"timing": "host wall clock around a synchronised call, L2 flushed "
-                     "(the reference path has host syncs and launches on the "
-                     "legacy default stream)",
+    out = {"timing": "host wall clock around a synchronised call, L2 flushed, "
+                     "median after 4 warm-up calls (the reference path has "
+                     "host syncs and launches on the legacy default stream)",
            "label": "reference (PyTorch restatement; mmcv MSDA kernel "
                     "unavailable -> its documented grid_sample equivalent)"}
     ref_step = 0.0
