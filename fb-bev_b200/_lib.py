@@ -51,9 +51,12 @@ _SIGNATURES = {
         ctypes.c_int, [_p] * 8 + [_i32, _i32, _i64, _p, _p, _p]),
     "fbbev_voxel_prepare_workspace_bytes": (_sz, [_i64, _i64]),
     "fbbev_voxel_prepare": (
-        ctypes.c_int, [_p] + [_i32] * 5 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+        ctypes.c_int, [_p] + [_i32] * 5 + [_p] * 3 + [_p] * 6 +
+        [_p, _sz, _i32, _p, _sz, _p]),
     "fbbev_voxel_prepare_cams": (
-        ctypes.c_int, [_p] * 8 + [_i32] * 6 + [_p] * 3 + [_p] * 6 + [_p, _sz, _p]),
+        ctypes.c_int, [_p] * 8 + [_i32] * 6 + [_p] * 3 + [_p] * 6 +
+        [_p, _sz, _i32, _p, _sz, _p]),
+    "fbbev_voxel_prepare_can_plan": (ctypes.c_int, [_i32, _i64]),
     "fbbev_point_sampling": (
         ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32] * 3 +
         [ctypes.c_float] * 4 + [_p] * 4),
@@ -78,7 +81,7 @@ _SIGNATURES = {
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

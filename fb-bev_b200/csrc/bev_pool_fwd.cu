@@ -402,6 +402,8 @@ static inline bool use_split(int c, int64_t zyx) {
   return pool_kernel_mode() == 1 && split_supported(c, zyx);
 }
 
+bool dense_uses_split(int c, int64_t zyx) { return use_split(c, zyx); }
+
 template <int T, int NW>
 static int launch_dense(const float* depth, const float* feat,
                         const int* ranks_depth, const int* ranks_feat,

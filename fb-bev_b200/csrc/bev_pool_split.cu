@@ -534,6 +534,20 @@ size_t split_workspace_bytes(int batch, int64_t zyx, int n_intervals_max,
       .bytes;
 }
 
+SplitPlanPtrs split_plan_ptrs(void* workspace, int batch, int64_t zyx,
+                              int n_intervals_max, int n_points_max, int c) {
+  const SplitWs w =
+      split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
+  SplitPlanPtrs p;
+  p.tile_first = w.tile_first; p.seg_rank = w.seg_rank;
+  p.warp_first = w.warp_first; p.meta = w.meta;
+  p.T = split_pick_tile(c);
+  p.tiles_per_b = (int)ceil_div64(zyx, p.T);
+  p.n_tiles = (int64_t)batch * p.tiles_per_b;
+  p.n_warps_max = w.n_warps_max;
+  return p;
+}
+
 int split_plan(const int* ranks_bev, const int* interval_starts,
                const int* interval_lengths, int n_intervals_max,
                const int* n_intervals_dev, int n_points_max, int c, int batch,

@@ -12,6 +12,18 @@ int split_plan(const int* ranks_bev, const int* interval_starts,
                const int* interval_lengths, int n_intervals_max,
                const int* n_intervals_dev, int n_points_max, int c, int batch,
                int64_t zyx, void* workspace, cudaStream_t st);
+// Where the plan tables of a dense-pooling workspace live, so that the index
+// builder (voxel_prepare.cu) can fill them while it scans the histogram
+// instead of a separate plan launch.
+struct SplitPlanPtrs {
+  int *tile_first, *seg_rank, *warp_first, *meta;
+  int T, tiles_per_b, n_warps_max;
+  int64_t n_tiles;
+};
+SplitPlanPtrs split_plan_ptrs(void* workspace, int batch, int64_t zyx,
+                              int n_intervals_max, int n_points_max, int c);
+// true when the dense op runs the two-kernel path for this shape
+bool dense_uses_split(int c, int64_t zyx);
 // stages: K1 (interval sums) and / or K2 (dense write, optionally + `add`, a
 // (B, C, yx_n) map broadcast over Z)
 constexpr int kSplitSums = 1, kSplitWrite = 2;

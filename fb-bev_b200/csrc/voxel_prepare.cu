@@ -21,6 +21,9 @@
 //     against the FLOAT32 grid size;
 //   * the rank is formed in exact integer arithmetic (the reference's float32
 //     arithmetic is identical below 2^24 voxels and wrong above).
+#include <algorithm>
+
+#include "bev_pool_split.h"
 #include "common.cuh"
 
 namespace fbbev {
@@ -176,32 +179,42 @@ __global__ void __launch_bounds__(kPrepThreads) prep_scan_reduce_kernel(
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of block_sums in place; totals -> counts
-__global__ void __launch_bounds__(kPrepThreads) prep_scan_spine_kernel(
-    int2* __restrict__ block_sums, int n_blocks, int* __restrict__ counts) {
-  __shared__ int2 wsum[kPrepThreads / kWarp];
-  int2 carry = make_int2(0, 0);
-  for (int base = 0; base < n_blocks; base += kPrepThreads) {
-    const int i = base + threadIdx.x;
-    const int2 mine = i < n_blocks ? block_sums[i] : make_int2(0, 0);
-    int2 v = mine;
-    const int2 total = block_incl_scan(v, wsum);
-    if (i < n_blocks)
-      block_sums[i] = make_int2(carry.x + v.x - mine.x, carry.y + v.y - mine.y);
-    carry.x += total.x;
-    carry.y += total.y;
-  }
-  if (threadIdx.x == 0) {
-    counts[0] = carry.x;  // n_kept
-    counts[1] = carry.y;  // n_intervals
-  }
-}
+// Plan tables of the dense pooling op (bev_pool_split.cu), filled here when a
+// pooling workspace is handed to the index builder: the scan below already
+// knows, for every voxel, how many intervals and points precede it --
+//   tile_first[t] = intervals before the tile's first voxel,
+//   seg_rank[i]   = voxel rank of interval i (the voxel index itself),
+//   warp_first[w] = first interval starting at or after point 32 w
+// -- which is all split_plan_kernel computes (with a binary search per slice
+// and a gap fill per interval) in a launch of its own.
+struct PlanOut {
+  int *tile_first, *seg_rank, *warp_first, *meta;  // tile_first == null: off
+  int T, tiles_per_b, n_warps_max;
+  int64_t zyx, n_tiles;
+};
 
+// Exclusive prefix of the block totals is formed by every block itself (<= a
+// few hundred int2 per block), which removes the single-block spine launch;
+// the last block also publishes the totals: counts = {n_kept, n_intervals}.
 __global__ void __launch_bounds__(kPrepThreads) prep_scan_apply_kernel(
     const int* __restrict__ hist, int64_t n_vox,
     const int2* __restrict__ block_sums, int* __restrict__ offset,
-    int* __restrict__ interval_starts, int* __restrict__ interval_lengths) {
+    int* __restrict__ interval_starts, int* __restrict__ interval_lengths,
+    int* __restrict__ counts, PlanOut plan) {
   __shared__ int2 wsum[kPrepThreads / kWarp];
+  __shared__ int2 s_prefix;
+  {  // prefix of the totals of the blocks before this one
+    int2 acc = make_int2(0, 0);
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += kPrepThreads) {
+      const int2 t = block_sums[j];
+      acc.x += t.x;
+      acc.y += t.y;
+    }
+    const int2 tot = block_incl_scan(acc, wsum);
+    if (threadIdx.x == 0) s_prefix = tot;
+    __syncthreads();
+  }
+  const int2 bs = s_prefix;
   // blocked arrangement: thread t owns kScanItems consecutive voxels
   const int64_t base =
       (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -215,21 +228,52 @@ __global__ void __launch_bounds__(kPrepThreads) prep_scan_apply_kernel(
     v.y += h[k] > 0;
   }
   const int2 mine = v;
-  block_incl_scan(v, wsum);
-  const int2 bs = block_sums[blockIdx.x];
+  const int2 block_total = block_incl_scan(v, wsum);
   int run_pts = bs.x + v.x - mine.x;  // exclusive prefix for this thread
   int run_int = bs.y + v.y - mine.y;
+  const bool planned = plan.tile_first != nullptr;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const int64_t i = base + k;
     if (i < n_vox) {
       offset[i] = run_pts;
+      if (planned) {
+        const int64_t b = i / plan.zyx, local = i - b * plan.zyx;
+        if (local % plan.T == 0)
+          plan.tile_first[b * plan.tiles_per_b + local / plan.T] = run_int;
+      }
       if (h[k] > 0) {
         interval_starts[run_int] = run_pts;   // view_transformer.py:597
         interval_lengths[run_int] = h[k];     // :599-602
+        if (planned) {
+          plan.seg_rank[run_int] = (int)i;
+          // slices w with run_pts < 32 w <= run_pts + h start inside or right
+          // after this interval: the first interval at or after them is the
+          // next one; a slice that starts exactly here gets this one
+          if (run_pts % kWarp == 0 && run_pts / kWarp <= plan.n_warps_max)
+            plan.warp_first[run_pts / kWarp] = run_int;
+          for (int w = run_pts / kWarp + 1;
+               w * kWarp <= run_pts + h[k] && w <= plan.n_warps_max; ++w)
+            if (w * kWarp > run_pts && w * kWarp < run_pts + h[k])
+              plan.warp_first[w] = run_int + 1;
+        }
         run_int++;
       }
       run_pts += h[k];
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    const int n_kept = bs.x + block_total.x, n_int = bs.y + block_total.y;
+    counts[0] = n_kept;
+    counts[1] = n_int;
+    if (planned) {
+      const int n_warps = min((n_kept + kWarp - 1) / kWarp, plan.n_warps_max);
+      plan.meta[0] = n_int;
+      plan.meta[1] = n_kept;
+      plan.meta[2] = n_warps;
+      plan.tile_first[plan.n_tiles] = n_int;
+      plan.warp_first[n_warps] = n_int;  // slices at / past the last point
+      if (n_int == 0) plan.warp_first[0] = 0;
     }
   }
 }
@@ -322,6 +366,7 @@ static int voxel_prepare_impl(
     const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
     int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
     int32_t* counts, void* workspace, size_t workspace_bytes,
+    int32_t pool_c, void* pool_plan, size_t pool_plan_bytes,
     fbbev_stream_t stream) {
   if (B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || !lo_host || !iv_host ||
       !gs_host)
@@ -353,7 +398,25 @@ static int voxel_prepare_impl(
   if (e != cudaSuccess) return (int)e;
   const unsigned pt_grid = (unsigned)ceil_div64(n_pts, kPrepThreads);
   const int n_scan_blocks = (int)ceil_div64(n_vox, kScanTile);
-  count_launch(6);
+  PlanOut plan;
+  plan.tile_first = nullptr;
+  if (pool_plan) {
+    const int64_t zyx = (int64_t)g.gx * g.gy * g.gz;
+    const int cap = (int)std::min<int64_t>(n_pts, n_vox);
+    if (pool_c <= 0 || !dense_uses_split(pool_c, zyx))
+      return FBBEV_ERR_UNSUPPORTED;
+    if (pool_plan_bytes < fbbev_bev_pool_v2_dense_workspace_bytes(
+                              B, zyx, cap, (int32_t)n_pts, pool_c))
+      return FBBEV_ERR_WORKSPACE_TOO_SMALL;
+    const SplitPlanPtrs pp =
+        split_plan_ptrs(pool_plan, B, zyx, cap, (int)n_pts, pool_c);
+    plan.tile_first = pp.tile_first; plan.seg_rank = pp.seg_rank;
+    plan.warp_first = pp.warp_first; plan.meta = pp.meta;
+    plan.T = pp.T; plan.tiles_per_b = pp.tiles_per_b;
+    plan.n_warps_max = pp.n_warps_max;
+    plan.zyx = zyx; plan.n_tiles = pp.n_tiles;
+  }
+  count_launch(5);
   if (coor)
     prep_voxelize_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
         coor, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
@@ -362,11 +425,9 @@ static int voxel_prepare_impl(
         *cg, n_pts, (int64_t)N * D * H * W, g, w.rank, w.hist);
   prep_scan_reduce_kernel<<<n_scan_blocks, kPrepThreads, 0, st>>>(
       w.hist, n_vox, w.block_sums);
-  prep_scan_spine_kernel<<<1, kPrepThreads, 0, st>>>(w.block_sums,
-                                                     n_scan_blocks, counts);
   prep_scan_apply_kernel<<<n_scan_blocks, kPrepThreads, 0, st>>>(
       w.hist, n_vox, w.block_sums, w.offset, interval_starts,
-      interval_lengths);
+      interval_lengths, counts, plan);
   prep_scatter_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
       w.rank, n_pts, w.offset, w.cursor, w.bucket);
   prep_order_kernel<<<pt_grid, kPrepThreads, 0, st>>>(
@@ -380,12 +441,14 @@ FBBEV_API int fbbev_voxel_prepare(
     const float* lo_host, const float* iv_host, const float* gs_host,
     int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
     int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts,
-    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
+    void* workspace, size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream) {
   if (!coor) return FBBEV_ERR_INVALID_ARGUMENT;
   return voxel_prepare_impl(coor, nullptr, B, N, D, H, W, lo_host, iv_host,
                             gs_host, ranks_bev, ranks_depth, ranks_feat,
                             interval_starts, interval_lengths, counts,
-                            workspace, workspace_bytes, stream);
+                            workspace, workspace_bytes, pool_c, pool_plan,
+                            pool_plan_bytes, stream);
 }
 
 FBBEV_API int fbbev_voxel_prepare_cams(
@@ -396,8 +459,8 @@ FBBEV_API int fbbev_voxel_prepare_cams(
     const float* iv_host,
     const float* gs_host, int32_t* ranks_bev, int32_t* ranks_depth,
     int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
-    int32_t* counts, void* workspace, size_t workspace_bytes,
-    fbbev_stream_t stream) {
+    int32_t* counts, void* workspace, size_t workspace_bytes, int32_t pool_c,
+    void* pool_plan, size_t pool_plan_bytes, fbbev_stream_t stream) {
   if (!frustum_u || !frustum_v || !frustum_d || !inv_post_rots ||
       !post_trans || !cam2ego || !trans || !bda)
     return FBBEV_ERR_INVALID_ARGUMENT;
@@ -410,5 +473,10 @@ FBBEV_API int fbbev_voxel_prepare_cams(
   return voxel_prepare_impl(nullptr, &cg, B, N, D, H, W, lo_host, iv_host,
                             gs_host, ranks_bev, ranks_depth, ranks_feat,
                             interval_starts, interval_lengths, counts,
-                            workspace, workspace_bytes, stream);
+                            workspace, workspace_bytes, pool_c, pool_plan,
+                            pool_plan_bytes, stream);
+}
+
+FBBEV_API int fbbev_voxel_prepare_can_plan(int32_t pool_c, int64_t zyx) {
+  return pool_c > 0 && zyx > 0 && dense_uses_split(pool_c, zyx) ? 1 : 0;
 }

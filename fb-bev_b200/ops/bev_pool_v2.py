@@ -95,9 +95,20 @@ class QuickCumsumCuda(torch.autograd.Function):
 KERNEL_HOOK = None
 
 
+def _usable_plan(plan, shape, n_points):
+    """A plan filled by the index builder fits this call when it was laid out
+    for the same volume / channel count (its workspace layout depends on them)."""
+    if plan is None:
+        return None
+    ws, nbytes, pshape, cap = plan
+    if tuple(pshape) != tuple(int(v) for v in shape):
+        return None
+    return ws, nbytes, cap
+
+
 def _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                    bev_feat_shape, interval_starts, interval_lengths,
-                   n_intervals_dev):
+                   n_intervals_dev, plan=None):
     dev = _lib.require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                             interval_starts, interval_lengths, n_intervals_dev)
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
@@ -124,18 +135,24 @@ def _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     # V[n_intervals][C] workspace of the sync-free path (whose index buffers
     # are n_points long) -- 1.7 GB -> 0.8 GB for 16 frames of 200x200x16
     n_int_cap = min(interval_lengths.shape[0], B * Z * Y * X)
-    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(
-        B, Z * Y * X, n_int_cap, n_points, C)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ready = _usable_plan(plan, (B, Z, Y, X, C), n_points)
+    if ready is not None and ready[2] == n_int_cap:
+        ws, ws_bytes, _ = ready            # planned by the index builder
+    else:
+        ready = None
+        ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(
+            B, Z * Y * X, n_int_cap, n_points, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     hook = KERNEL_HOOK
     with torch.cuda.device(dev):
         sp = _lib.stream_ptr(dev)
-        rc = L.fbbev_bev_pool_v2_plan(
-            _lib.ptr(ranks_bev), _lib.ptr(interval_starts),
-            _lib.ptr(interval_lengths), n_int_cap,
-            _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X, _lib.ptr(ws),
-            ws_bytes, sp)
-        _lib.check(rc, 'fbbev_bev_pool_v2_plan')
+        if ready is None:
+            rc = L.fbbev_bev_pool_v2_plan(
+                _lib.ptr(ranks_bev), _lib.ptr(interval_starts),
+                _lib.ptr(interval_lengths), n_int_cap,
+                _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X,
+                _lib.ptr(ws), ws_bytes, sp)
+            _lib.check(rc, 'fbbev_bev_pool_v2_plan')
         if hook is not None:
             hook.before()
         rc = L.fbbev_bev_pool_v2_fwd_dense_planned(
@@ -156,7 +173,7 @@ class _BevPoolV2Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev,
                 bev_feat_shape, interval_starts, interval_lengths,
-                n_intervals_dev, n_kept_dev):
+                n_intervals_dev, n_kept_dev, plan=None):
         ranks_bev = ranks_bev.contiguous().int()
         depth = depth.contiguous().float()
         feat = feat.contiguous().float()
@@ -166,7 +183,7 @@ class _BevPoolV2Dense(torch.autograd.Function):
         interval_starts = interval_starts.contiguous().int()
         out = _dense_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                              bev_feat_shape, interval_starts, interval_lengths,
-                             n_intervals_dev)
+                             n_intervals_dev, plan)
         ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth,
                               n_kept_dev)
         ctx.has_count = n_kept_dev is not None
@@ -199,12 +216,12 @@ class _BevPoolV2Dense(torch.autograd.Function):
                     _lib.ptr(depth_grad), _lib.ptr(feat_grad),
                     _lib.stream_ptr(dev))
             _lib.check(rc, 'fbbev_bev_pool_v2_bwd_bczyx')
-        return (depth_grad, feat_grad) + (None,) * 8
+        return (depth_grad, feat_grad) + (None,) * 9
 
 
 def bev_pool_v2_dense(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                       bev_feat_shape, interval_starts, interval_lengths,
-                      n_intervals_dev=None, n_kept_dev=None):
+                      n_intervals_dev=None, n_kept_dev=None, plan=None):
     """Fused ``bev_pool_v2``: returns contiguous ``(B, C, Z, Y, X)``.
 
     ``n_intervals_dev`` / ``n_kept_dev`` (0-dim int32 CUDA tensors) mark the
@@ -213,7 +230,8 @@ def bev_pool_v2_dense(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     """
     return _BevPoolV2Dense.apply(depth, feat, ranks_depth, ranks_feat,
                                  ranks_bev, bev_feat_shape, interval_starts,
-                                 interval_lengths, n_intervals_dev, n_kept_dev)
+                                 interval_lengths, n_intervals_dev, n_kept_dev,
+                                 plan)
 
 
 class DeferredVolume:
@@ -280,7 +298,7 @@ def deferred_supported(bev_feat_shape):
 
 def bev_pool_v2_deferred(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                          bev_feat_shape, interval_starts, interval_lengths,
-                         n_intervals_dev=None):
+                         n_intervals_dev=None, plan=None):
     """Plan + interval sums of the dense op; returns a :class:`DeferredVolume`
     (``fbbev_bev_pool_v2_plan`` + ``fbbev_bev_pool_v2_sums_planned``)."""
     dev = _lib.require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev,
@@ -295,15 +313,21 @@ def bev_pool_v2_deferred(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     L = _lib.lib()
     n_points = rb.shape[0]
     cap = min(ln.shape[0], B * Z * Y * X)
-    ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, Z * Y * X, cap,
-                                                         n_points, C)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ready = _usable_plan(plan, (B, Z, Y, X, C), n_points)
+    if ready is not None and ready[2] == cap:
+        ws, ws_bytes, _ = ready
+    else:
+        ready = None
+        ws_bytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, Z * Y * X, cap,
+                                                             n_points, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         sp = _lib.stream_ptr(dev)
-        _lib.check(L.fbbev_bev_pool_v2_plan(
-            _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), cap,
-            _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X, _lib.ptr(ws),
-            ws_bytes, sp), 'fbbev_bev_pool_v2_plan')
+        if ready is None:
+            _lib.check(L.fbbev_bev_pool_v2_plan(
+                _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), cap,
+                _lib.ptr(n_intervals_dev), n_points, C, B, Z * Y * X,
+                _lib.ptr(ws), ws_bytes, sp), 'fbbev_bev_pool_v2_plan')
         _lib.check(L.fbbev_bev_pool_v2_sums_planned(
             _lib.ptr(depth), _lib.ptr(feat), _lib.ptr(rd), _lib.ptr(rf),
             _lib.ptr(rb), _lib.ptr(st), _lib.ptr(ln), cap, n_points, C, B,
@@ -336,13 +360,16 @@ class VoxelIndex:
     """
 
     def __init__(self, ranks_bev, ranks_depth, ranks_feat, interval_starts,
-                 interval_lengths, counts):
+                 interval_lengths, counts, plan=None):
         self.ranks_bev = ranks_bev
         self.ranks_depth = ranks_depth
         self.ranks_feat = ranks_feat
         self.interval_starts = interval_starts
         self.interval_lengths = interval_lengths
         self.counts = counts
+        # (workspace, bytes, shape (B, Z, Y, X, C), n_int_cap) of a dense-pooling
+        # plan the index builder filled while scanning (no plan launch needed)
+        self.plan = plan
 
     @property
     def n_kept_dev(self):
@@ -363,12 +390,32 @@ class VoxelIndex:
                 self.interval_lengths[:n_int])
 
 
-def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
+def _plan_workspace(L, dev, B, gs, n_pts, pool_channels):
+    """Dense-pooling workspace for the index builder to fill the plan into, or
+    ``(None, 0, None)`` when the shape is not covered."""
+    if not pool_channels:
+        return None, 0, None
+    X, Y, Z = int(gs[0]), int(gs[1]), int(gs[2])
+    zyx = Z * Y * X
+    C = int(pool_channels)
+    if C > 512 or B * zyx > 2 ** 31 - 1 or \
+            not L.fbbev_voxel_prepare_can_plan(C, zyx):
+        return None, 0, None
+    cap = min(n_pts, B * zyx)
+    nbytes = L.fbbev_bev_pool_v2_dense_workspace_bytes(B, zyx, cap, n_pts, C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return ws, nbytes, (ws, nbytes, (B, Z, Y, X, C), cap)
+
+
+def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size,
+                             pool_channels=None):
     """Device ``voxel_pooling_prepare_v2`` (view_transformer.py:547-605).
 
     coor ``(B,N,D,H,W,3)`` fp32 CUDA; the three grid descriptors are the
     3-element float32 tensors of ``create_grid_infos`` (:384-387) -- host
-    tensors or python sequences.  Returns a :class:`VoxelIndex`.
+    tensors or python sequences.  Returns a :class:`VoxelIndex`;
+    ``pool_channels`` = C of the pooling call that will consume the index lets
+    the builder fill that call's plan on the way (``VoxelIndex.plan``).
     """
     dev = _lib.require_cuda(coor)
     coor = coor.contiguous().float()
@@ -384,20 +431,22 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
     counts = torch.empty(2, dtype=torch.int32, device=dev)
     ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    pws, pbytes, plan = _plan_workspace(L, dev, B, gs, n_pts, pool_channels)
     with torch.cuda.device(dev):
         rc = L.fbbev_voxel_prepare(
             _lib.ptr(coor), B, N, D, H, W, _lib.c_floats(lo), _lib.c_floats(iv),
             _lib.c_floats(gs), _lib.ptr(idx[0]), _lib.ptr(idx[1]),
             _lib.ptr(idx[2]), _lib.ptr(idx[3]), _lib.ptr(idx[4]),
-            _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+            _lib.ptr(counts), _lib.ptr(ws), ws_bytes, int(pool_channels or 0),
+            _lib.ptr(pws), pbytes, _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_voxel_prepare')
-    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts)
+    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts, plan)
 
 
 def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
                                     cam2ego, trans, bda, depth_bins,
                                     grid_lower_bound, grid_interval,
-                                    grid_size):
+                                    grid_size, pool_channels=None):
     """``get_lidar_coor`` + ``voxel_pooling_prepare_v2`` in one pass
     (view_transformer.py:458-498, 547-605): the (B,N,D,H,W,3) coordinate
     tensor is never materialised (``fbbev_voxel_prepare_cams``).
@@ -426,6 +475,7 @@ def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
     counts = torch.empty(2, dtype=torch.int32, device=dev)
     ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    pws, pbytes, plan = _plan_workspace(L, dev, B, gs, n_pts, pool_channels)
     with torch.cuda.device(dev):
         rc = L.fbbev_voxel_prepare_cams(
             _lib.ptr(fu), _lib.ptr(fv), _lib.ptr(fd), _lib.ptr(mats[0]),
@@ -434,6 +484,7 @@ def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
             _lib.c_floats(iv), _lib.c_floats(gs), _lib.ptr(idx[0]),
             _lib.ptr(idx[1]), _lib.ptr(idx[2]), _lib.ptr(idx[3]),
             _lib.ptr(idx[4]), _lib.ptr(counts), _lib.ptr(ws), ws_bytes,
+            int(pool_channels or 0), _lib.ptr(pws), pbytes,
             _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_voxel_prepare_cams')
-    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts)
+    return VoxelIndex(idx[0], idx[1], idx[2], idx[3], idx[4], counts, plan)

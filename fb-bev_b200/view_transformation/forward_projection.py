@@ -157,7 +157,7 @@ class _LSSBase(BaseModule):
         return cache[key]
 
     def prepare_index_from_cams(self, rots, trans, cam2imgs, post_rots,
-                                post_trans, bda):
+                                post_trans, bda, pool_channels=None):
         """Index straight from the camera parameters (fused geometry).  The
         two 3x3 products the reference forms before touching the points
         (view_transformer.py:483-491) are formed here by the same torch ops
@@ -168,13 +168,16 @@ class _LSSBase(BaseModule):
         return voxel_pooling_prepare_from_cams(
             self._frustum_axes(rots.device), inv_pr, post_trans, cam2ego,
             trans, bda, self.D, self.grid_lower_bound, self.grid_interval,
-            self.grid_size)
+            self.grid_size, pool_channels=pool_channels)
 
     # -- view_transformer.py:547-605 ------------------------------------
-    def prepare_index(self, coor):
-        """Device-resident index of ``coor`` (no host sync)."""
+    def prepare_index(self, coor, pool_channels=None):
+        """Device-resident index of ``coor`` (no host sync).  ``pool_channels``:
+        the channel count of the pooling call that follows, so that the index
+        builder can fill that call's plan while it scans."""
         return voxel_pooling_prepare_v2(coor, self.grid_lower_bound,
-                                        self.grid_interval, self.grid_size)
+                                        self.grid_interval, self.grid_size,
+                                        pool_channels=pool_channels)
 
     def voxel_pooling_prepare_v2(self, coor):
         """Same return contract as the reference: five exact-length int32
@@ -213,7 +216,8 @@ class _LSSBase(BaseModule):
             return bev_pool_v2_dense(
                 depth, feat, idx.ranks_depth, idx.ranks_feat, idx.ranks_bev,
                 shape, idx.interval_starts, idx.interval_lengths,
-                n_intervals_dev=idx.n_intervals_dev, n_kept_dev=idx.n_kept_dev)
+                n_intervals_dev=idx.n_intervals_dev, n_kept_dev=idx.n_kept_dev,
+                plan=idx.plan)
         rb, rd, rf, st, ln = idx
         return bev_pool_v2(depth, feat, rd, rf, rb, shape, st, ln)
 
@@ -261,11 +265,13 @@ class LSSViewTransformerFunction3D(_LSSBase):
         if self.accelerate:
             bev_feat = self._pool(self._index, depth, tran_feat)
             return bev_feat.permute(0, 1, 3, 4, 2)
+        C = tran_feat.shape[2]
         if self.fused_geometry:
-            idx = self.prepare_index_from_cams(*cam_params)
+            idx = self.prepare_index_from_cams(*cam_params, pool_channels=C)
             return self._pool(idx, depth, tran_feat).permute(0, 1, 3, 4, 2)
         coor = self.get_lidar_coor(*cam_params)
-        return self.voxel_pooling_v2(coor, depth, tran_feat)
+        idx = self.prepare_index(coor, pool_channels=C)
+        return self._pool(idx, depth, tran_feat).permute(0, 1, 3, 4, 2)
 
     def view_transform(self, cam_params, depth, tran_feat):
         if self.accelerate:
@@ -290,13 +296,15 @@ class LSSViewTransformerFunction3D(_LSSBase):
             self.pre_compute(cam_params)
             idx = self._index
         elif self.fused_geometry:
-            idx = self.prepare_index_from_cams(*cam_params)
+            idx = self.prepare_index_from_cams(*cam_params,
+                                               pool_channels=shape[-1])
         else:
-            idx = self.prepare_index(self.get_lidar_coor(*cam_params))
+            idx = self.prepare_index(self.get_lidar_coor(*cam_params),
+                                     pool_channels=shape[-1])
         return bev_pool_v2_deferred(
             depth, feat, idx.ranks_depth, idx.ranks_feat, idx.ranks_bev, shape,
             idx.interval_starts, idx.interval_lengths,
-            n_intervals_dev=idx.n_intervals_dev)
+            n_intervals_dev=idx.n_intervals_dev, plan=idx.plan)
 
     # -- view_transformer.py:646-660 ------------------------------------
     def forward(self, cam_params, context, depth, **kwargs):

@@ -31,7 +31,7 @@ extern "C" {
 #define FBBEV_ERR_WORKSPACE_TOO_SMALL (-2)
 #define FBBEV_ERR_UNSUPPORTED (-3)
 
-#define FBBEV_ABI_VERSION 2
+#define FBBEV_ABI_VERSION 3
 
 typedef void* fbbev_stream_t; /* cudaStream_t */
 
@@ -207,7 +207,8 @@ int fbbev_voxel_prepare(const float* coor, int32_t B, int32_t N, int32_t D,
                         int32_t* ranks_bev, int32_t* ranks_depth,
                         int32_t* ranks_feat, int32_t* interval_starts,
                         int32_t* interval_lengths, int32_t* counts,
-                        void* workspace, size_t workspace_bytes,
+                        void* workspace, size_t workspace_bytes, int32_t pool_c,
+                        void* pool_plan, size_t pool_plan_bytes,
                         fbbev_stream_t stream);
 
 /*
@@ -225,7 +226,17 @@ int fbbev_voxel_prepare(const float* coor, int32_t B, int32_t N, int32_t D,
  * column-major matrix (the layout torch.inverse returns) is broadcast over the
  * whole batch.  order_flags: bit 0 inv_post_rots, bit 1 cam2ego, bit 2 bda.
  * The index is bit-identical to fbbev_voxel_prepare on get_lidar_coor's output.
+ *
+ * pool_plan (both prepare entry points; may be NULL): a dense-pooling workspace
+ * of fbbev_bev_pool_v2_dense_workspace_bytes(B, Z*Y*X, min(n_points, B*Z*Y*X),
+ * n_points, pool_c) bytes.  When given, the scan over the voxel histogram also
+ * fills the pooling plan (what fbbev_bev_pool_v2_plan computes in a launch of
+ * its own), so the index can go straight to fbbev_bev_pool_v2_fwd_dense_planned
+ * / _sums_planned with the same workspace and n_intervals_max = min(n_points,
+ * B*Z*Y*X).  Needs fbbev_voxel_prepare_can_plan(pool_c, Z*Y*X) != 0, else
+ * FBBEV_ERR_UNSUPPORTED.
  */
+int fbbev_voxel_prepare_can_plan(int32_t pool_c, int64_t n_voxels_per_sample);
 #define FBBEV_ORDER_SEQ_A 1
 #define FBBEV_ORDER_SEQ_B 2
 #define FBBEV_ORDER_SEQ_C 4
@@ -237,7 +248,8 @@ int fbbev_voxel_prepare_cams(
     const float* iv_host, const float* gs_host, int32_t* ranks_bev,
     int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
     int32_t* interval_lengths, int32_t* counts, void* workspace,
-    size_t workspace_bytes, fbbev_stream_t stream);
+    size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream);
 
 /* =====================================================================
  * B -- BEV -> image depth-aware spatial cross-attention (MSDeformAttn)
