@@ -67,7 +67,9 @@ _SIGNATURES = {
     "fbbev_msda_fused_fwd": (ctypes.c_int, [_p] * 6 + [_i32] * 8 + [_p, _p]),
     "fbbev_da_sca_workspace_bytes": (_sz, [_i32, _i32]),
     "fbbev_da_sca_fwd": (ctypes.c_int,
-                         [_p] * 10 + [_i32] * 10 + [_p, _p, _sz, _p]),
+                         [_p] * 10 + [_i32] * 10 + [_p, _p, _sz, _i32, _p]),
+    "fbbev_da_sca_prologue": (ctypes.c_int,
+                              [_p] + [_i32] * 9 + [_p, _p, _sz, _p]),
     "fbbev_history_warp": (ctypes.c_int, [_p, _i64, _p] + [_i32] * 5 +
                            [_p, _i32, _i32, _p]),
     "fbbev_linear_packed_bytes": (ctypes.c_size_t, [_i32, _i32]),

@@ -411,7 +411,8 @@ int da_sca_smem_launch(const float* value, const float* depth_prob,
                        const uint8_t* mask, const float* offsets,
                        const float* logits, const int64_t* shapes, float d_min,
                        float d_step, int bs, int n_cams, int nq, int n_value,
-                       int DC, float* out, void* workspace, cudaStream_t st) {
+                       int DC, float* out, void* workspace, cudaStream_t st,
+                       int stages) {
   ScaSmemParams P;
   P.value = value; P.depth_prob = depth_prob; P.ref_cam = ref_cam;
   P.ref_depth = ref_depth; P.offsets = offsets; P.logits = logits;
@@ -429,10 +430,15 @@ int da_sca_smem_launch(const float* value, const float* depth_prob,
   const int64_t n_out4 = (int64_t)bs * nq * kE / 4;
   const int zero_blocks = (int)std::min<int64_t>(ceil_div64(n_out4, 256 * 4),
                                                  (int64_t)n_sm * 16);
-  count_launch(2);
-  da_sca_prologue_kernel<<<P.n_pairs * kCountChunks + zero_blocks, 256, 0, st>>>(
-      P.mask32, bs, n_cams, nq, static_cast<int*>(workspace),
-      reinterpret_cast<float4*>(out), n_out4);
+  if (stages & kScaPrologue) {
+    count_launch();
+    da_sca_prologue_kernel<<<P.n_pairs * kCountChunks + zero_blocks, 256, 0,
+                             st>>>(P.mask32, bs, n_cams, nq,
+                                   static_cast<int*>(workspace),
+                                   reinterpret_cast<float4*>(out), n_out4);
+    if (!(stages & kScaMain)) return launch_status();
+  }
+  count_launch();
   // 512 or 640 threads per CTA (FBBEV_SCA_THREADS: tuning aid)
   static int threads = 0;
   if (threads == 0) {

@@ -391,6 +391,27 @@ FBBEV_API size_t fbbev_da_sca_workspace_bytes(int32_t bs, int32_t n_cams) {
   return da_sca_smem_workspace_bytes(bs, n_cams);
 }
 
+// The part of fbbev_da_sca_fwd that depends on the mask only (visible-query
+// counts per camera, zero-fill of `out`): callable ahead of time, e.g. on the
+// stream that produced the mask.  Returns FBBEV_ERR_UNSUPPORTED when the shape
+// takes the global-memory kernel (which has no prologue).
+FBBEV_API int fbbev_da_sca_prologue(const uint8_t* mask, int32_t bs,
+                                    int32_t n_cams, int32_t nq, int32_t n_value,
+                                    int32_t heads, int32_t ch, int32_t levels,
+                                    int32_t points, int32_t Z, float* out,
+                                    void* workspace, size_t workspace_bytes,
+                                    fbbev_stream_t stream) {
+  if (bs <= 0 || nq <= 0 || n_cams <= 0 || !mask || !out || !workspace)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < da_sca_smem_workspace_bytes(bs, n_cams) ||
+      !da_sca_smem_eligible(n_cams, n_value, heads, ch, levels, points, Z) ||
+      bs * n_cams > 4096 || (reinterpret_cast<uintptr_t>(out) & 15))
+    return FBBEV_ERR_UNSUPPORTED;
+  return da_sca_smem_launch(nullptr, nullptr, nullptr, nullptr, mask, nullptr,
+                            nullptr, nullptr, 0.f, 1.f, bs, n_cams, nq, n_value,
+                            1, out, workspace, as_stream(stream), kScaPrologue);
+}
+
 FBBEV_API int fbbev_msda_fwd(const float* value, const int64_t* spatial_shapes,
                              const int64_t* level_start, const float* loc,
                              const float* attw, int32_t bs, int32_t n_value,
@@ -485,7 +506,8 @@ FBBEV_API int fbbev_da_sca_fwd(
     const int64_t* level_start, const float* dbound_host, int32_t bs,
     int32_t n_cams, int32_t nq, int32_t n_value, int32_t heads, int32_t ch,
     int32_t levels, int32_t points, int32_t Z, int32_t DC, float* out,
-    void* workspace, size_t workspace_bytes, fbbev_stream_t stream) {
+    void* workspace, size_t workspace_bytes, int32_t prologue_done,
+    fbbev_stream_t stream) {
   if (bs < 0 || nq < 0 || n_cams <= 0 || n_value <= 0 || heads <= 0 ||
       ch <= 0 || levels <= 0 || points <= 0 || Z <= 0 || DC <= 0 ||
       !dbound_host || points % Z != 0)
@@ -510,7 +532,10 @@ FBBEV_API int fbbev_da_sca_fwd(
     return da_sca_smem_launch(value, depth_prob, ref_cam, ref_depth, mask,
                               offsets, logits, spatial_shapes, P.d_min,
                               P.d_step, bs, n_cams, nq, n_value, DC, out,
-                              workspace, st);
+                              workspace, st,
+                              prologue_done ? kScaMain
+                                            : (kScaPrologue | kScaMain));
+  if (prologue_done) return FBBEV_ERR_INVALID_ARGUMENT;  // no such stage here
   count_launch();
 #define FBBEV_LAUNCH_Z(CHV, ZV)                                              \
   da_sca_fwd_kernel<CHV, ZV><<<grid, kMsdaThreads, 0, st>>>(                 \

@@ -21,7 +21,8 @@ __all__ = ['MultiScaleDeformableAttnFunction_fp32',
            'MultiScaleDeformableAttnFunction_fp16', 'ms_deform_attn_forward',
            'ms_deform_attn_fused', 'ms_deform_attn_unfused',
            'da_spatial_cross_attention_core',
-           'da_spatial_cross_attention_core_autograd', 'point_sampling',
+           'da_spatial_cross_attention_core_autograd', 'da_sca_prepare',
+           'point_sampling',
            'bev_query_init', 'tokens_to_map',
            'needs_grad']
 
@@ -202,11 +203,40 @@ def da_spatial_cross_attention_core_autograd(
     return slots / count[..., None]
 
 
+def _mask_u8(per_cam_mask):
+    mask = per_cam_mask.contiguous()
+    return mask if mask.dtype == torch.uint8 else mask.view(torch.uint8) \
+        if mask.dtype == torch.bool else mask.to(torch.uint8)
+
+
+def da_sca_prepare(per_cam_mask, bs, nq, n_value, heads, ch, levels, points, Z):
+    """The mask-only part of the camera-resident cross-attention (per-camera
+    visible-query counts, zero-filled output): ``fbbev_da_sca_prologue``.  The
+    encoder runs it on its side stream right after ``point_sampling``; the
+    result goes to :func:`da_spatial_cross_attention_core` as ``prepared``.
+    Returns None when the shape takes the global-memory kernel."""
+    dev = _lib.require_cuda(per_cam_mask)
+    mask = _mask_u8(per_cam_mask)
+    n_cams = mask.shape[0]
+    L = _lib.lib()
+    ws_bytes = L.fbbev_da_sca_workspace_bytes(bs, n_cams)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    out = torch.empty((bs, nq, heads * ch), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.fbbev_da_sca_prologue(
+            _lib.ptr(mask), bs, n_cams, nq, n_value, heads, ch, levels, points,
+            Z, _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+    if rc == -3:        # FBBEV_ERR_UNSUPPORTED: global-memory kernel, no prologue
+        return None
+    _lib.check(rc, 'fbbev_da_sca_prologue')
+    return out, ws, ws_bytes, mask
+
+
 def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
                                     bev_query_depth, per_cam_mask,
                                     sampling_offsets, attention_logits,
                                     spatial_shapes, level_start_index, dbound,
-                                    num_Z_anchors):
+                                    num_Z_anchors, prepared=None):
     """Fused depth-aware spatial cross-attention between the input Linears and
     ``output_proj`` (spatial_cross_attention_depth.py:156-216, 540-595).
 
@@ -225,9 +255,7 @@ def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
     depth_prob = depth_prob.contiguous().float()
     ref = reference_points_cam.contiguous().float()
     rdep = bev_query_depth.contiguous().float()
-    mask = per_cam_mask.contiguous()
-    if mask.dtype != torch.uint8:
-        mask = mask.to(torch.uint8)
+    mask = _mask_u8(per_cam_mask) if prepared is None else prepared[3]
     off = sampling_offsets.contiguous().float()
     lg = attention_logits.contiguous().float()
     ss, ls = _i64(spatial_shapes, dev), _i64(level_start_index, dev)
@@ -236,17 +264,22 @@ def da_spatial_cross_attention_core(value, depth_prob, reference_points_cam,
     assert bn == bs * n_cams and Z == num_Z_anchors
     _, _, _, levels, points, _ = off.shape
     DC = depth_prob.shape[-1]
-    out = value.new_empty((bs, nq, heads * ch))
     L = _lib.lib()
-    ws_bytes = L.fbbev_da_sca_workspace_bytes(bs, n_cams)
-    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    if prepared is not None:
+        out, ws, ws_bytes, _ = prepared
+        assert tuple(out.shape) == (bs, nq, heads * ch)
+    else:
+        out = value.new_empty((bs, nq, heads * ch))
+        ws_bytes = L.fbbev_da_sca_workspace_bytes(bs, n_cams)
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = L.fbbev_da_sca_fwd(
             _lib.ptr(value), _lib.ptr(depth_prob), _lib.ptr(ref),
             _lib.ptr(rdep), _lib.ptr(mask), _lib.ptr(off), _lib.ptr(lg),
             _lib.ptr(ss), _lib.ptr(ls), _lib.c_floats(dbound), bs, n_cams, nq,
             n_value, heads, ch, levels, points, Z, DC, _lib.ptr(out),
-            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+            _lib.ptr(ws), ws_bytes, 1 if prepared is not None else 0,
+            _lib.stream_ptr(dev))
     _lib.check(rc, 'fbbev_da_sca_fwd')
     return out
 

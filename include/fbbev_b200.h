@@ -394,7 +394,18 @@ int fbbev_da_sca_fwd(const float* value, const float* depth_prob,
                      int32_t bs, int32_t n_cams, int32_t nq, int32_t n_value,
                      int32_t heads, int32_t ch, int32_t levels, int32_t points,
                      int32_t Z, int32_t DC, float* out, void* workspace,
-                     size_t workspace_bytes, fbbev_stream_t stream);
+                     size_t workspace_bytes, int32_t prologue_done,
+                     fbbev_stream_t stream);
+/* The mask-only part of fbbev_da_sca_fwd's camera-resident path (per-camera
+ * visible-query counts into `workspace`, zero-fill of `out`), callable ahead of
+ * time -- e.g. on the stream that produced the mask, beside the self-attention.
+ * Pass the same `out` / `workspace` to fbbev_da_sca_fwd with prologue_done = 1.
+ * FBBEV_ERR_UNSUPPORTED when the shape takes the global-memory kernel. */
+int fbbev_da_sca_prologue(const uint8_t* mask, int32_t bs, int32_t n_cams,
+                          int32_t nq, int32_t n_value, int32_t heads,
+                          int32_t ch, int32_t levels, int32_t points, int32_t Z,
+                          float* out, void* workspace, size_t workspace_bytes,
+                          fbbev_stream_t stream);
 
 /* ---- row-wise Linear (+ bias, ReLU, residual, LayerNorm) on tcgen05 ---------
  * Replaces the nn.Linear / LayerNorm / residual chain of the reference's

@@ -44,7 +44,8 @@ def msda_fused_cpu(value, spatial_shapes, level_start_index, reference_points,
 
 def da_sca_core_cpu(value, depth_prob, reference_points_cam, bev_query_depth,
                     per_cam_mask, sampling_offsets, attention_logits,
-                    spatial_shapes, level_start_index, dbound, num_Z_anchors):
+                    spatial_shapes, level_start_index, dbound, num_Z_anchors,
+                    prepared=None):
     """Same contract as ``fbbev_da_sca_fwd`` / ops.da_spatial_cross_attention_core.
 
     value (bs*N, n_value, heads, ch); depth_prob (bs*N, H0*W0, DC);

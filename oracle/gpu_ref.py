@@ -104,7 +104,8 @@ def msda_fused_eager(value, spatial_shapes, level_start_index,
 
 def da_sca_core_eager(value, depth_prob, reference_points_cam, bev_query_depth,
                       per_cam_mask, sampling_offsets, attention_logits,
-                      spatial_shapes, level_start_index, dbound, num_Z_anchors):
+                      spatial_shapes, level_start_index, dbound, num_Z_anchors,
+                    prepared=None):
     """spatial_cross_attention_depth.py:156-216 + 540-595 with eager ops on the
     tensors' device (same contract as ops.da_spatial_cross_attention_core)."""
     shapes = spatial_shapes.tolist()

@@ -49,7 +49,7 @@ def test_argument_validation_without_gpu():
     assert L.fbbev_msda_fwd(None, None, None, None, None, 1, 10, 8, 7, 1, 5,
                             4, None, None) == -1             # NULL pointers
     assert L.fbbev_da_sca_fwd(*([None] * 10), 1, 6, 10, 10, 8, 10, 1, 7, 4,
-                              80, None, None, 0, None) == -1  # points % Z != 0
+                              80, None, None, 0, 0, None) == -1  # points % Z != 0
     assert L.fbbev_da_sca_workspace_bytes(2, 6) >= 2 * 6 * 4
 
 

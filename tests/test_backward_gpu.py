@@ -433,7 +433,7 @@ def test_da_sca_smem_kernel_vs_global_kernel_and_oracle(bs, nq, hw):
         _lib.ptr(v), _lib.ptr(dp), _lib.ptr(r), _lib.ptr(qd),
         _lib.ptr(mk.to(torch.uint8)), _lib.ptr(o), _lib.ptr(l), _lib.ptr(s),
         _lib.ptr(lsi), _lib.c_floats(dbound), bs, N, nq, H * W, heads, ch, L, P,
-        Z, DC, _lib.ptr(out), None, 0, _lib.stream_ptr(torch.device(DEV)))
+        Z, DC, _lib.ptr(out), None, 0, 0, _lib.stream_ptr(torch.device(DEV)))
     assert rc == 0
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=2e-5)
