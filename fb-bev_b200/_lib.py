@@ -57,6 +57,17 @@ _SIGNATURES = {
         ctypes.c_int, [_p] * 8 + [_i32] * 6 + [_p] * 3 + [_p] * 6 +
         [_p, _sz, _i32, _p, _sz, _p]),
     "fbbev_voxel_prepare_can_plan": (ctypes.c_int, [_i32, _i64]),
+    "fbbev_voxel_prepare_sparse": (
+        ctypes.c_int, [_p, _p, ctypes.c_float] + [_i32] * 5 + [_p] * 3 +
+        [_p] * 6 + [_p, _sz, _i32, _p, _sz, _p]),
+    "fbbev_voxel_prepare_cams_sparse": (
+        ctypes.c_int, [_p] * 8 + [_i32, _p, ctypes.c_float] + [_i32] * 5 +
+        [_p] * 3 + [_p] * 6 + [_p, _sz, _i32, _p, _sz, _p]),
+    "fbbev_lift_tail_fwd": (
+        ctypes.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "fbbev_bev_mask_fold_workspace_bytes": (_sz, [_i32, _i32]),
+    "fbbev_bev_mask_fold": (
+        ctypes.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "fbbev_point_sampling": (
         ctypes.c_int, [_p] * 3 + [_i32] * 3 + [_p] * 5 + [_i32] * 3 +
         [ctypes.c_float] * 4 + [_p] * 4),
@@ -83,7 +94,7 @@ _SIGNATURES = {
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

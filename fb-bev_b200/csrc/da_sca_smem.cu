@@ -167,7 +167,7 @@ __device__ __forceinline__ void sca_pass(const ScaSmemParams& P, const ScaCtx& C
   // cameras that see this query (:213-216): lane m asks for camera m
   const bool cam_sees =
       active && m < P.n_cams &&
-      __ldg(P.mask32 + ((int64_t)m * P.bs + C.b) * P.nq + q) != 0;
+      (__ldg(P.mask32 + ((int64_t)m * P.bs + C.b) * P.nq + q) & 0x01010101u) != 0;
   const unsigned cb = __ballot_sync(kFull, cam_sees);
   const float cnt = (float)max(1, __popc((cb >> (slot * 8)) & 0xffu));
 

@@ -246,3 +246,93 @@ FBBEV_API int fbbev_point_sampling(
                           as_stream(stream)>>>(P, ref_cam, depth, mask);
   return launch_status();
 }
+
+// ---------------------------------------------------------------------------
+// per_cam_mask & bev_mask for the fused cross-attention
+//   DA_SpatialCrossAttention.forward, spatial_cross_attention_depth.py:156-169:
+//     per_cam_mask_list_ = per_cam_mask_list & bev_mask[None, :, :, None]
+//     index = per_cam_mask_[j].sum(-1).nonzero()
+//     if len(index) == 0: index = per_cam_mask_list[i][j].sum(-1).nonzero()[0:1]
+// and :213-214  count = per_cam_mask_list_.sum(-1) > 0.
+// Output bytes: 1 = anchor visible under the masked list (the query is
+// processed for that camera AND counted), 2 = the empty-camera rule: the first
+// query the camera sees at all is processed although bev_mask excludes it, and
+// is not counted.  The attention kernels test `byte != 0` for visibility and
+// `byte & 1` for the count.
+// ---------------------------------------------------------------------------
+namespace fbbev {
+
+__global__ void bev_mask_fold_init_kernel(int* any_first, int n_pairs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pairs) {
+    any_first[i] = 0;
+    any_first[n_pairs + i] = INT32_MAX;
+  }
+}
+
+__global__ void __launch_bounds__(256) bev_mask_fold_kernel(
+    const uint8_t* __restrict__ mask, const uint8_t* __restrict__ bev_mask,
+    int bs, int nq, int Z, int n_pairs, uint8_t* __restrict__ out,
+    int* __restrict__ any_first) {
+  const int pair = blockIdx.y;          // n * bs + b
+  const int b = pair % bs;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  bool vis = false, kept = false;
+  if (q < nq) {
+    const int64_t base = ((int64_t)pair * nq + q) * Z;
+    const bool bev = __ldg(bev_mask + (int64_t)b * nq + q) != 0;
+    for (int z = 0; z < Z; ++z) {
+      const bool m = __ldg(mask + base + z) != 0;
+      vis |= m;
+      out[base + z] = (m && bev) ? 1 : 0;
+    }
+    kept = vis && bev;
+  }
+  const unsigned any_kept = __ballot_sync(kFull, kept);
+  const int first = __reduce_min_sync(kFull, vis ? q : INT32_MAX);
+  if ((threadIdx.x & 31) == 0) {
+    if (any_kept) any_first[pair] = 1;                   // benign race: all write 1
+    if (first != INT32_MAX) atomicMin(any_first + n_pairs + pair, first);
+  }
+}
+
+__global__ void bev_mask_fold_fix_kernel(const uint8_t* __restrict__ mask, int nq,
+                                         int Z, int n_pairs,
+                                         const int* __restrict__ any_first,
+                                         uint8_t* __restrict__ out) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  const int q0 = any_first[n_pairs + pair];
+  if (any_first[pair] != 0 || q0 == INT32_MAX) return;
+  const int64_t base = ((int64_t)pair * nq + q0) * Z;
+  for (int z = 0; z < Z; ++z) out[base + z] = mask[base + z] != 0 ? 2 : 0;
+}
+
+}  // namespace fbbev
+
+FBBEV_API size_t fbbev_bev_mask_fold_workspace_bytes(int32_t bs, int32_t n_cams) {
+  if (bs <= 0 || n_cams <= 0) return 0;
+  return (size_t)bs * n_cams * 2 * sizeof(int);
+}
+
+FBBEV_API int fbbev_bev_mask_fold(const uint8_t* mask, const uint8_t* bev_mask,
+                                  int32_t bs, int32_t n_cams, int32_t nq,
+                                  int32_t Z, uint8_t* mask_out, void* workspace,
+                                  size_t workspace_bytes, fbbev_stream_t stream) {
+  if (!mask || !bev_mask || !mask_out || !workspace || bs <= 0 || n_cams <= 0 ||
+      nq <= 0 || Z <= 0)
+    return FBBEV_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < fbbev_bev_mask_fold_workspace_bytes(bs, n_cams))
+    return FBBEV_ERR_WORKSPACE_TOO_SMALL;
+  const int n_pairs = bs * n_cams;
+  if (n_pairs > 65535) return FBBEV_ERR_UNSUPPORTED;
+  int* af = static_cast<int*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  count_launch(3);
+  bev_mask_fold_init_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(af, n_pairs);
+  bev_mask_fold_kernel<<<dim3((nq + 255) / 256, n_pairs), 256, 0, st>>>(
+      mask, bev_mask, bs, nq, Z, n_pairs, mask_out, af);
+  bev_mask_fold_fix_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(
+      mask, nq, Z, n_pairs, af, mask_out);
+  return launch_status();
+}

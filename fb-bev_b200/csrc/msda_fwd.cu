@@ -313,11 +313,14 @@ __global__ void __launch_bounds__(kMsdaThreads) da_sca_fwd_kernel(
 
   for (int n = 0; n < P.n_cams; ++n) {
     const int64_t rbase = (((int64_t)n * P.bs + b) * P.nq + q) * Z;
-    bool seen = false;  // per_cam_mask[j].sum(-1) > 0   (:165)
+    // per_cam_mask[j].sum(-1) > 0 (:165).  Mask bytes: bit 0 = visible and
+    // counted; 2 = visible through the empty-camera rule of a bev_mask
+    // (fbbev_bev_mask_fold): processed, not counted (:166-167, :213-214)
+    unsigned seen = 0;
 #pragma unroll
-    for (int z = 0; z < Z; ++z) seen |= __ldg(mask + rbase + z) != 0;
+    for (int z = 0; z < Z; ++z) seen |= __ldg(mask + rbase + z);
     if (!seen) continue;
-    ++count;
+    count += (int)(seen & 1u);
     if (!have_softmax) {
       softmax_stats(logits + wbase, LP, mx, inv);  // :540
       have_softmax = true;

@@ -35,6 +35,11 @@ constexpr int kScanTile = kPrepThreads * kScanItems;  // per block
 struct GridParams {
   float lo[3], iv[3], gs[3];
   int gx, gy, gz;
+  // depth-threshold sparsification of the BEVDet lineage
+  // (necks/view_transformer.py:556-557: kept &= depth.view(-1) > 0.01); the
+  // depth tensor is indexed by the point index itself (ranks_depth == arange)
+  const float* depth_prob;  // null: keep every in-grid point
+  float depth_thresh;
 };
 
 // `.long()` of the CUDA device the reference runs on: cvt.rzi.s64.f32
@@ -54,7 +59,9 @@ __device__ __forceinline__ void voxelize_point(float x, float y, float z,
   const long long cz = trunc_i64(__fdiv_rn(__fsub_rn(z, g.lo[2]), g.iv[2]));
   const bool keep = cx >= 0 && (float)cx < g.gs[0] && cy >= 0 &&
                     (float)cy < g.gs[1] && cz >= 0 && (float)cz < g.gs[2] &&
-                    cx < g.gx && cy < g.gy && cz < g.gz;
+                    cx < g.gx && cy < g.gy && cz < g.gz &&
+                    (g.depth_prob == nullptr ||
+                     __ldg(g.depth_prob + p) > g.depth_thresh);
   int r = -1;
   if (keep) {
     const int64_t b = p / per_b;
@@ -367,7 +374,7 @@ static int voxel_prepare_impl(
     int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
     int32_t* counts, void* workspace, size_t workspace_bytes,
     int32_t pool_c, void* pool_plan, size_t pool_plan_bytes,
-    fbbev_stream_t stream) {
+    const float* depth_prob, float depth_thresh, fbbev_stream_t stream) {
   if (B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || !lo_host || !iv_host ||
       !gs_host)
     return FBBEV_ERR_INVALID_ARGUMENT;
@@ -385,6 +392,8 @@ static int voxel_prepare_impl(
   g.gx = (int)gs_host[0];  // int(self.grid_size[i]), view_transformer.py:537-538
   g.gy = (int)gs_host[1];
   g.gz = (int)gs_host[2];
+  g.depth_prob = depth_prob;
+  g.depth_thresh = depth_thresh;
   const int64_t n_pts = (int64_t)B * N * D * H * W;
   const int64_t n_vox = (int64_t)B * g.gx * g.gy * g.gz;
   if (n_pts > INT32_MAX || n_vox > INT32_MAX) return FBBEV_ERR_UNSUPPORTED;
@@ -436,6 +445,22 @@ static int voxel_prepare_impl(
   return launch_status();
 }
 
+FBBEV_API int fbbev_voxel_prepare_sparse(
+    const float* coor, const float* depth_prob, float depth_thresh, int32_t B,
+    int32_t N, int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host, const float* gs_host, int32_t* ranks_bev,
+    int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int32_t* counts, void* workspace,
+    size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream) {
+  if (!coor) return FBBEV_ERR_INVALID_ARGUMENT;
+  return voxel_prepare_impl(coor, nullptr, B, N, D, H, W, lo_host, iv_host,
+                            gs_host, ranks_bev, ranks_depth, ranks_feat,
+                            interval_starts, interval_lengths, counts,
+                            workspace, workspace_bytes, pool_c, pool_plan,
+                            pool_plan_bytes, depth_prob, depth_thresh, stream);
+}
+
 FBBEV_API int fbbev_voxel_prepare(
     const float* coor, int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
     const float* lo_host, const float* iv_host, const float* gs_host,
@@ -443,12 +468,10 @@ FBBEV_API int fbbev_voxel_prepare(
     int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts,
     void* workspace, size_t workspace_bytes, int32_t pool_c, void* pool_plan,
     size_t pool_plan_bytes, fbbev_stream_t stream) {
-  if (!coor) return FBBEV_ERR_INVALID_ARGUMENT;
-  return voxel_prepare_impl(coor, nullptr, B, N, D, H, W, lo_host, iv_host,
-                            gs_host, ranks_bev, ranks_depth, ranks_feat,
-                            interval_starts, interval_lengths, counts,
-                            workspace, workspace_bytes, pool_c, pool_plan,
-                            pool_plan_bytes, stream);
+  return fbbev_voxel_prepare_sparse(
+      coor, nullptr, 0.f, B, N, D, H, W, lo_host, iv_host, gs_host, ranks_bev,
+      ranks_depth, ranks_feat, interval_starts, interval_lengths, counts,
+      workspace, workspace_bytes, pool_c, pool_plan, pool_plan_bytes, stream);
 }
 
 FBBEV_API int fbbev_voxel_prepare_cams(
@@ -461,6 +484,25 @@ FBBEV_API int fbbev_voxel_prepare_cams(
     int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
     int32_t* counts, void* workspace, size_t workspace_bytes, int32_t pool_c,
     void* pool_plan, size_t pool_plan_bytes, fbbev_stream_t stream) {
+  return fbbev_voxel_prepare_cams_sparse(
+      frustum_u, frustum_v, frustum_d, inv_post_rots, post_trans, cam2ego,
+      trans, bda, order_flags, nullptr, 0.f, B, N, D, H, W, lo_host, iv_host,
+      gs_host, ranks_bev, ranks_depth, ranks_feat, interval_starts,
+      interval_lengths, counts, workspace, workspace_bytes, pool_c, pool_plan,
+      pool_plan_bytes, stream);
+}
+
+FBBEV_API int fbbev_voxel_prepare_cams_sparse(
+    const float* frustum_u, const float* frustum_v, const float* frustum_d,
+    const float* inv_post_rots, const float* post_trans, const float* cam2ego,
+    const float* trans, const float* bda, int32_t order_flags,
+    const float* depth_prob, float depth_thresh, int32_t B, int32_t N,
+    int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host, const float* gs_host, int32_t* ranks_bev,
+    int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int32_t* counts, void* workspace,
+    size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream) {
   if (!frustum_u || !frustum_v || !frustum_d || !inv_post_rots ||
       !post_trans || !cam2ego || !trans || !bda)
     return FBBEV_ERR_INVALID_ARGUMENT;
@@ -474,7 +516,7 @@ FBBEV_API int fbbev_voxel_prepare_cams(
                             gs_host, ranks_bev, ranks_depth, ranks_feat,
                             interval_starts, interval_lengths, counts,
                             workspace, workspace_bytes, pool_c, pool_plan,
-                            pool_plan_bytes, stream);
+                            pool_plan_bytes, depth_prob, depth_thresh, stream);
 }
 
 FBBEV_API int fbbev_voxel_prepare_can_plan(int32_t pool_c, int64_t zyx) {

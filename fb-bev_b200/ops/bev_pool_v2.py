@@ -407,8 +407,19 @@ def _plan_workspace(L, dev, B, gs, n_pts, pool_channels):
     return ws, nbytes, (ws, nbytes, (B, Z, Y, X, C), cap)
 
 
+def _depth_arg(depth, n_pts, dev):
+    """Contiguous fp32 depth tensor for the depth-threshold sparsification
+    (necks/view_transformer.py:556-557), or None."""
+    if depth is None:
+        return None
+    d = depth.detach().contiguous().float()
+    assert d.numel() == n_pts and d.device == dev
+    return d
+
+
 def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size,
-                             pool_channels=None):
+                             pool_channels=None, depth=None,
+                             depth_thresh=0.01):
     """Device ``voxel_pooling_prepare_v2`` (view_transformer.py:547-605).
 
     coor ``(B,N,D,H,W,3)`` fp32 CUDA; the three grid descriptors are the
@@ -416,6 +427,9 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size,
     tensors or python sequences.  Returns a :class:`VoxelIndex`;
     ``pool_channels`` = C of the pooling call that will consume the index lets
     the builder fill that call's plan on the way (``VoxelIndex.plan``).
+    ``depth`` (B,N,D,H,W): additionally drop the points whose depth
+    probability is <= ``depth_thresh`` -- LSSViewTransformer2's sparsification
+    (necks/view_transformer.py:556-557).
     """
     dev = _lib.require_cuda(coor)
     coor = coor.contiguous().float()
@@ -432,9 +446,11 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size,
     ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     pws, pbytes, plan = _plan_workspace(L, dev, B, gs, n_pts, pool_channels)
+    dprob = _depth_arg(depth, n_pts, dev)
     with torch.cuda.device(dev):
-        rc = L.fbbev_voxel_prepare(
-            _lib.ptr(coor), B, N, D, H, W, _lib.c_floats(lo), _lib.c_floats(iv),
+        rc = L.fbbev_voxel_prepare_sparse(
+            _lib.ptr(coor), _lib.ptr(dprob), float(depth_thresh), B, N, D, H,
+            W, _lib.c_floats(lo), _lib.c_floats(iv),
             _lib.c_floats(gs), _lib.ptr(idx[0]), _lib.ptr(idx[1]),
             _lib.ptr(idx[2]), _lib.ptr(idx[3]), _lib.ptr(idx[4]),
             _lib.ptr(counts), _lib.ptr(ws), ws_bytes, int(pool_channels or 0),
@@ -446,7 +462,8 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size,
 def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
                                     cam2ego, trans, bda, depth_bins,
                                     grid_lower_bound, grid_interval,
-                                    grid_size, pool_channels=None):
+                                    grid_size, pool_channels=None, depth=None,
+                                    depth_thresh=0.01):
     """``get_lidar_coor`` + ``voxel_pooling_prepare_v2`` in one pass
     (view_transformer.py:458-498, 547-605): the (B,N,D,H,W,3) coordinate
     tensor is never materialised (``fbbev_voxel_prepare_cams``).
@@ -476,11 +493,13 @@ def voxel_pooling_prepare_from_cams(frustum_axes, inv_post_rots, post_trans,
     ws_bytes = L.fbbev_voxel_prepare_workspace_bytes(n_pts, n_vox)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     pws, pbytes, plan = _plan_workspace(L, dev, B, gs, n_pts, pool_channels)
+    dprob = _depth_arg(depth, n_pts, dev)
     with torch.cuda.device(dev):
-        rc = L.fbbev_voxel_prepare_cams(
+        rc = L.fbbev_voxel_prepare_cams_sparse(
             _lib.ptr(fu), _lib.ptr(fv), _lib.ptr(fd), _lib.ptr(mats[0]),
             _lib.ptr(mats[1]), _lib.ptr(mats[2]), _lib.ptr(mats[3]),
-            _lib.ptr(mats[4]), order, B, N, D, H, W, _lib.c_floats(lo),
+            _lib.ptr(mats[4]), order, _lib.ptr(dprob), float(depth_thresh), B,
+            N, D, H, W, _lib.c_floats(lo),
             _lib.c_floats(iv), _lib.c_floats(gs), _lib.ptr(idx[0]),
             _lib.ptr(idx[1]), _lib.ptr(idx[2]), _lib.ptr(idx[3]),
             _lib.ptr(idx[4]), _lib.ptr(counts), _lib.ptr(ws), ws_bytes,

@@ -197,9 +197,13 @@ def da_spatial_cross_attention_core_autograd(
         bs * N, nq, heads, L, P) * dw[:, :, None, None, :]      # :592
     out = apply(value, spatial_shapes, level_start_index, loc, wts,
                 im2col_step).view(bs, N, nq, E)
-    seen = per_cam_mask.bool().any(-1).permute(1, 0, 2)      # (bs, N, nq)
+    # mask bytes: != 0 visible, bit 0 counted (see bev_mask_fold)
+    m8 = per_cam_mask if per_cam_mask.dtype == torch.uint8 else \
+        per_cam_mask.to(torch.uint8)
+    seen = (m8 != 0).any(-1).permute(1, 0, 2)                # (bs, N, nq)
+    counted = ((m8 & 1) != 0).any(-1).permute(1, 0, 2)
     slots = (out * seen[..., None].to(out.dtype)).sum(1)
-    count = seen.sum(1).clamp(min=1).to(out.dtype)
+    count = counted.sum(1).clamp(min=1).to(out.dtype)
     return slots / count[..., None]
 
 
@@ -207,6 +211,31 @@ def _mask_u8(per_cam_mask):
     mask = per_cam_mask.contiguous()
     return mask if mask.dtype == torch.uint8 else mask.view(torch.uint8) \
         if mask.dtype == torch.bool else mask.to(torch.uint8)
+
+
+def bev_mask_fold(per_cam_mask, bev_mask):
+    """``per_cam_mask_list & bev_mask[None, :, :, None]`` with the reference's
+    empty-camera rule (spatial_cross_attention_depth.py:156-169, 213-214) as a
+    device-side pass (``fbbev_bev_mask_fold``): the result goes to the fused
+    cross-attention as its mask (1 = visible and counted, 2 = visible, not
+    counted), so a ``bev_mask`` needs no nonzero() / re-batching loops.
+    per_cam_mask (n_cams, bs, nq, Z) bool / uint8; bev_mask (bs, nq)."""
+    dev = _lib.require_cuda(per_cam_mask, bev_mask)
+    mask = _mask_u8(per_cam_mask)
+    bev = _mask_u8(bev_mask != 0 if bev_mask.dtype not in
+                   (torch.bool, torch.uint8) else bev_mask)
+    n_cams, bs, nq, Z = mask.shape
+    assert tuple(bev.shape) == (bs, nq)
+    L = _lib.lib()
+    out = torch.empty_like(mask)
+    ws_bytes = L.fbbev_bev_mask_fold_workspace_bytes(bs, n_cams)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.fbbev_bev_mask_fold(_lib.ptr(mask), _lib.ptr(bev), bs, n_cams,
+                                   nq, Z, _lib.ptr(out), _lib.ptr(ws),
+                                   ws_bytes, _lib.stream_ptr(dev))
+    _lib.check(rc, 'fbbev_bev_mask_fold')
+    return out
 
 
 def da_sca_prepare(per_cam_mask, bs, nq, n_value, heads, ch, levels, points, Z):

@@ -4,3 +4,5 @@ registers them (see ``registry.py``)."""
 from .forward_projection import *  # noqa: F401,F403
 from .backward_projection import *  # noqa: F401,F403
 from .temporal_fusion import *  # noqa: F401,F403
+from .bevdet_lineage import *  # noqa: F401,F403
+from .depth_net_tail import *  # noqa: F401,F403

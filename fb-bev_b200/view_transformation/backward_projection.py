@@ -47,6 +47,7 @@ from ..ops import linear as _linear_ops
 from .forward_projection import inv3x3_many
 from ..ops import ms_deform_attn as _msda_ops
 from ..ops.ms_deform_attn import (MultiScaleDeformableAttnFunction_fp32,
+                                  bev_mask_fold,
                                   da_spatial_cross_attention_core,
                                   da_spatial_cross_attention_core_autograd,
                                   ms_deform_attn_fused, ms_deform_attn_unfused,
@@ -490,7 +491,15 @@ class DA_MSDeformableAttention(BaseModule):
 @register('ATTENTION')
 class DA_SpatialCrossAttention(BaseModule):
     """Depth-aware spatial cross-attention of the BEV queries over the camera
-    feature maps."""
+    feature maps.
+
+    ``rebatch_bev_mask`` (class attribute, default False): with a ``bev_mask``
+    run the reference-shaped per-camera re-batching loops (``nonzero()`` host
+    synchronisations) instead of folding the mask on the device and running
+    the fused kernel -- kept as the literal restatement the fused route is
+    tested against."""
+
+    rebatch_bev_mask = False
 
     def __init__(self, embed_dims=256, num_cams=6, pc_range=None, dropout=0.1,
                  init_cfg=None, batch_first=False,
@@ -551,13 +560,20 @@ class DA_SpatialCrossAttention(BaseModule):
         side_event = kwargs.get('side_event')
         if side_event is not None and query.is_cuda:
             torch.cuda.current_stream(query.device).wait_event(side_event)
+        sca_prepared = (kwargs.get('sca_prepared') or {}).get(id(self))
         if bev_mask is not None:
-            if query_pos is not None:
-                query = query + query_pos.float()
-            return self._forward_rebatch(
-                query, value, inp_residual, key_padding_mask, spatial_shapes,
-                reference_points_cam, level_start_index, bev_query_depth,
-                pred_img_depth, bev_mask, per_cam_mask_list, post_norm)
+            if self.rebatch_bev_mask or not query.is_cuda:
+                if query_pos is not None:
+                    query = query + query_pos.float()
+                return self._forward_rebatch(
+                    query, value, inp_residual, key_padding_mask,
+                    spatial_shapes, reference_points_cam, level_start_index,
+                    bev_query_depth, pred_img_depth, bev_mask,
+                    per_cam_mask_list, post_norm)
+            # the masked list (:156-169) as a device-side pass: the fused
+            # kernels then run exactly as without a bev_mask
+            per_cam_mask_list = bev_mask_fold(per_cam_mask_list, bev_mask)
+            sca_prepared = None    # counts were taken on the unmasked list
 
         da = self.deformable_attention
         B, N, DC, H, W = pred_img_depth.shape
@@ -579,7 +595,7 @@ class DA_SpatialCrossAttention(BaseModule):
                 v, depth_prob, reference_points_cam, bev_query_depth,
                 per_cam_mask_list, offsets, logits, spatial_shapes,
                 level_start_index, self.dbound, da.num_Z_anchors,
-                prepared=(kwargs.get('sca_prepared') or {}).get(id(self)))
+                prepared=sca_prepared)
         return self._finish(slots, inp_residual, post_norm)
 
     def project_camera_value(self, value):

@@ -208,9 +208,13 @@ class _LSSBase(BaseModule):
         return (depth.shape[0], int(self.grid_size[2]), int(self.grid_size[1]),
                 int(self.grid_size[0]), feat_nhwc.shape[-1])  # (B, Z, Y, X, C)
 
-    def _pool(self, idx, depth, feat):
-        """depth (B,N,D,H,W), feat (B,N,C,H,W) -> (B,C,Z,Y,X) contiguous."""
-        feat = feat.permute(0, 1, 3, 4, 2)
+    def _pool(self, idx, depth, feat, nhwc=False):
+        """depth (B,N,D,H,W), feat (B,N,C,H,W) -- or, ``nhwc``, already the
+        (B,N,H,W,C) tensor ``bev_pool_v2`` reads (ops.lift_tail produces it, so
+        the permute + ``contiguous()`` copy of view_transformer.py:530 /
+        bev_pool.py:19 never runs) -> (B,C,Z,Y,X) contiguous."""
+        if not nhwc:
+            feat = feat.permute(0, 1, 3, 4, 2)
         shape = self._bev_feat_shape(depth, feat)
         if isinstance(idx, VoxelIndex):
             return bev_pool_v2_dense(
@@ -261,22 +265,23 @@ class LSSViewTransformerFunction3D(_LSSBase):
         return bev_feat.permute(0, 1, 3, 4, 2)
 
     # -- view_transformer.py:613-643 ------------------------------------
-    def view_transform_core(self, cam_params, depth, tran_feat):
+    def view_transform_core(self, cam_params, depth, tran_feat, nhwc=False):
         if self.accelerate:
-            bev_feat = self._pool(self._index, depth, tran_feat)
+            bev_feat = self._pool(self._index, depth, tran_feat, nhwc)
             return bev_feat.permute(0, 1, 3, 4, 2)
-        C = tran_feat.shape[2]
+        C = tran_feat.shape[-1 if nhwc else 2]
         if self.fused_geometry:
             idx = self.prepare_index_from_cams(*cam_params, pool_channels=C)
-            return self._pool(idx, depth, tran_feat).permute(0, 1, 3, 4, 2)
+            return self._pool(idx, depth, tran_feat, nhwc).permute(
+                0, 1, 3, 4, 2)
         coor = self.get_lidar_coor(*cam_params)
         idx = self.prepare_index(coor, pool_channels=C)
-        return self._pool(idx, depth, tran_feat).permute(0, 1, 3, 4, 2)
+        return self._pool(idx, depth, tran_feat, nhwc).permute(0, 1, 3, 4, 2)
 
-    def view_transform(self, cam_params, depth, tran_feat):
+    def view_transform(self, cam_params, depth, tran_feat, nhwc=False):
         if self.accelerate:
             self.pre_compute(cam_params)
-        return self.view_transform_core(cam_params, depth, tran_feat)
+        return self.view_transform_core(cam_params, depth, tran_feat, nhwc)
 
     def forward_deferred(self, cam_params, context, depth):
         """Index + interval sums only: a :class:`~..ops.bev_pool_v2.
@@ -307,10 +312,16 @@ class LSSViewTransformerFunction3D(_LSSBase):
             n_intervals_dev=idx.n_intervals_dev, plan=idx.plan)
 
     # -- view_transformer.py:646-660 ------------------------------------
-    def forward(self, cam_params, context, depth, **kwargs):
+    def forward(self, cam_params, context, depth, context_layout='nchw',
+                **kwargs):
         """cam_params = (rots, trans, intrins, post_rots, post_trans, bda);
-        context (B,N,C,H,W); depth (B,N,D,H,W) -> (B, C, Y, X, Z)."""
-        bev = self.view_transform(cam_params, depth, context)
+        context (B,N,C,H,W); depth (B,N,D,H,W) -> (B, C, Y, X, Z).
+        ``context_layout='nhwc'``: context is already (B,N,H,W,C), the layout
+        the pooling op reads (``CM_DepthNetTail`` / ``ops.lift_tail`` produce
+        it), and the op's own permute + copy is skipped."""
+        assert context_layout in ('nchw', 'nhwc')
+        bev = self.view_transform(cam_params, depth, context,
+                                  context_layout == 'nhwc')
         if self.extra_relu:
             return bev.relu()
         return bev

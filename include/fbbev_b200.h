@@ -31,7 +31,7 @@ extern "C" {
 #define FBBEV_ERR_WORKSPACE_TOO_SMALL (-2)
 #define FBBEV_ERR_UNSUPPORTED (-3)
 
-#define FBBEV_ABI_VERSION 3
+#define FBBEV_ABI_VERSION 4
 
 typedef void* fbbev_stream_t; /* cudaStream_t */
 
@@ -251,6 +251,61 @@ int fbbev_voxel_prepare_cams(
     size_t workspace_bytes, int32_t pool_c, void* pool_plan,
     size_t pool_plan_bytes, fbbev_stream_t stream);
 
+/*
+ * The same two index builders with the depth-threshold sparsification of the
+ * BEVDet-lineage transformer
+ *   mmdet3d/models/necks/view_transformer.py:520-578 (LSSViewTransformer2.
+ *   voxel_pooling_prepare_v2: `kept = kept & (depth.view(-1) > 0.01)`, :556-557)
+ *   and its cached-index form (:645-678: the geometric index filtered by
+ *   `(depth.view(-1) > 0.01)[self.kept]` on every forward).
+ * depth_prob (B,N,D,H,W) fp32 -- the tensor the pooling op will read, indexed
+ * by the point index (ranks_depth == arange) -- may be NULL (no threshold);
+ * a point is kept when depth_prob[p] > depth_thresh (strict, as the reference).
+ * Everything else as fbbev_voxel_prepare / fbbev_voxel_prepare_cams.
+ */
+int fbbev_voxel_prepare_sparse(
+    const float* coor, const float* depth_prob, float depth_thresh, int32_t B,
+    int32_t N, int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host, const float* gs_host, int32_t* ranks_bev,
+    int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int32_t* counts, void* workspace,
+    size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream);
+int fbbev_voxel_prepare_cams_sparse(
+    const float* frustum_u, const float* frustum_v, const float* frustum_d,
+    const float* inv_post_rots, const float* post_trans, const float* cam2ego,
+    const float* trans, const float* bda, int32_t order_flags,
+    const float* depth_prob, float depth_thresh, int32_t B, int32_t N,
+    int32_t D, int32_t H, int32_t W, const float* lo_host,
+    const float* iv_host, const float* gs_host, int32_t* ranks_bev,
+    int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int32_t* counts, void* workspace,
+    size_t workspace_bytes, int32_t pool_c, void* pool_plan,
+    size_t pool_plan_bytes, fbbev_stream_t stream);
+
+/*
+ * The tail of the depth net as the PRODUCER of the pooling op's inputs
+ * (SURVEY.md section 8 f4 / f3):
+ *   CM_DepthNet.forward   mmdet3d/models/fbbev/modules/depth_net.py:359-363
+ *       depth = depth.softmax(dim=1); context.view(B, N, C, H, W)
+ *   LSSViewTransformer / LSSViewTransformer2 / LSSViewTransformerBEVDepth.forward
+ *       mmdet3d/models/necks/view_transformer.py:313-321, 710-718, 1094-1096
+ *       depth_digit = x[:, :D]; tran_feat = x[:, D:D+C]; depth = softmax(dim=1)
+ *   + the `feat.permute(0,1,3,4,2)` / `feat.contiguous()` transposing copy inside
+ *     the pooling op (view_transformer.py:530, bev_pool.py:19).
+ * depth_logits: image n, bin k, pixel p at [n * logits_image_stride + k*hw + p]
+ * (NCHW with its own image stride, so a channel slice of a wider tensor works);
+ * context likewise with c channels.  Either may be NULL (that half is skipped).
+ * depth_out (bn, d, hw) = softmax over the d bins (max / sum of expf / divide,
+ * as torch); feat_out (bn, hw, c) = context transposed to pixel-major -- the
+ * (B,N,H,W,C) layout `bev_pool_v2` reads.  One launch.
+ */
+int fbbev_lift_tail_fwd(const float* depth_logits, int64_t logits_image_stride,
+                        const float* context, int64_t context_image_stride,
+                        int32_t bn, int32_t d, int32_t c, int32_t hw,
+                        float* depth_out, float* feat_out,
+                        fbbev_stream_t stream);
+
 /* =====================================================================
  * B -- BEV -> image depth-aware spatial cross-attention (MSDeformAttn)
  * ===================================================================== */
@@ -372,7 +427,9 @@ int fbbev_msda_fused_fwd(const float* value, const int64_t* spatial_shapes,
  * dbound_host = (d_min, d_max, d_step) (:196); DC = depth bins.
  * out        (bs, nq, heads*ch) = slots / clamp(count, 1), the tensor the
  *            reference feeds to output_proj (:219).
- * bev_mask (:156-159) is not supported by this entry point (NULL only).
+ * bev_mask (:156-159): pass the output of fbbev_bev_mask_fold as `mask`.
+ * Mask bytes: 0 = not visible; bit 0 set = visible and counted in the camera
+ * mean; 2 = visible but not counted (the reference's empty-camera rule).
  *
  * workspace (fbbev_da_sca_workspace_bytes(bs, n_cams) bytes, may be NULL):
  * with it, and when one camera's value map fits in shared memory (n_value *
@@ -406,6 +463,22 @@ int fbbev_da_sca_prologue(const uint8_t* mask, int32_t bs, int32_t n_cams,
                           int32_t ch, int32_t levels, int32_t points, int32_t Z,
                           float* out, void* workspace, size_t workspace_bytes,
                           fbbev_stream_t stream);
+
+/*
+ * `per_cam_mask_list & bev_mask[None, :, :, None]` with the reference's
+ * empty-camera rule (spatial_cross_attention_depth.py:156-169, 213-214) as a
+ * device-side pass, so a bev_mask no longer forces the per-camera nonzero() /
+ * re-batching loops (6*bs host synchronisations per layer in the reference).
+ * mask (n_cams, bs, nq, Z) uint8/bool; bev_mask (bs, nq) uint8/bool; mask_out
+ * (n_cams, bs, nq, Z) uint8 in the encoding fbbev_da_sca_fwd documents:
+ * 1 where mask & bev_mask; for a (sample, camera) pair that sees no query under
+ * the masked list, the anchors of the FIRST query it sees at all get 2.
+ */
+size_t fbbev_bev_mask_fold_workspace_bytes(int32_t bs, int32_t n_cams);
+int fbbev_bev_mask_fold(const uint8_t* mask, const uint8_t* bev_mask,
+                        int32_t bs, int32_t n_cams, int32_t nq, int32_t Z,
+                        uint8_t* mask_out, void* workspace,
+                        size_t workspace_bytes, fbbev_stream_t stream);
 
 /* ---- row-wise Linear (+ bias, ReLU, residual, LayerNorm) on tcgen05 ---------
  * Replaces the nn.Linear / LayerNorm / residual chain of the reference's

@@ -258,10 +258,18 @@ def main():
         ref_import.install_stubs()
         gen_fuse_history()
         return
+    if os.environ.get("GOLDEN_ONLY", "") == "lineage":
+        import gen_golden_lineage
+        gen_golden_lineage.gen_lineage(save)
+        return
     ref = ref_import.load_reference()
     torch.manual_seed(0)
     if os.environ.get("GOLDEN_ONLY", "") == "f2d":
         gen_forward_2d(ref)
+        return
+    if os.environ.get("GOLDEN_ONLY", "") == "backward":
+        import gen_golden_backward
+        gen_golden_backward.gen_backward(ref, save)
         return
     gen_forward(ref)
     gen_forward_2d(ref)

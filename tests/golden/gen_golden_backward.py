@@ -108,6 +108,23 @@ def gen_backward(ref, save):
                      pred_img_depth=depth)
         sca.forward = orig
 
+        # bev_mask (spatial_cross_attention_depth.py:156-169): (a) a random
+        # half of the BEV cells; (b) every cell camera 0 sees is excluded, so
+        # camera 0's masked list is empty and the reference's empty-camera
+        # rule (:166-167) adds its first visible query, uncounted
+        per_cam = cap['per_cam_mask_list']                 # (N, B, nq, Z)
+        gm = torch.Generator().manual_seed(seed + 7)
+        mask_a = torch.rand(B, bev_h * bev_w, generator=gm) > 0.5
+        mask_b = ~per_cam[0].any(-1)
+        assert per_cam[0].any() and (per_cam & mask_b[None, :, :, None]).any()
+        with torch.no_grad():
+            out_a = bp(mlvl, None, lss_bev=lss_bev, cam_params=cam,
+                       pred_img_depth=depth,
+                       bev_mask=mask_a.view(B, bev_h, bev_w))
+            out_b = bp(mlvl, None, lss_bev=lss_bev, cam_params=cam,
+                       pred_img_depth=depth,
+                       bev_mask=mask_b.view(B, bev_h, bev_w))
+
         sd = {'sd::' + k: _np(v) for k, v in bp.state_dict().items()}
         arrays = dict(
             bev_h=np.array(bev_h), bev_w=np.array(bev_w), E=np.array(E),
@@ -125,7 +142,9 @@ def gen_backward(ref, save):
             per_cam_mask=_np(cap['per_cam_mask_list']),
             spatial_shapes=_np(cap['spatial_shapes']),
             level_start_index=_np(cap['level_start_index']),
-            sca_out=_np(cap['out']), **sd)
+            sca_out=_np(cap['out']),
+            bev_mask_a=_np(mask_a), out_bev_mask_a=_np(out_a),
+            bev_mask_b=_np(mask_b), out_bev_mask_b=_np(out_b), **sd)
         for i, f in enumerate(mlvl):
             arrays[f'feat{i}'] = _np(f)
         save(name, **arrays)

@@ -30,7 +30,7 @@ def test_header_symbols_all_exported():
 def test_abi_version_and_error_strings():
     from fbbev_b200 import _lib
     L = _lib.lib()
-    assert L.fbbev_abi_version() == 3
+    assert L.fbbev_abi_version() == 4
     assert L.fbbev_error_string(0) == b"ok"
     assert b"workspace" in L.fbbev_error_string(-2)
     assert L.fbbev_bev_pool_v2_dense_workspace_bytes(1, 640000, 1000, 2000, 80) >= 4 * (

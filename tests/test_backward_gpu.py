@@ -146,7 +146,13 @@ def test_da_sca_rebatch_path_equals_fused(case):
     with torch.no_grad():
         fused = sca(q, k, k, None, **kw)
         mask = torch.ones(q.shape[:2], dtype=torch.bool, device=DEV)
+        sca.rebatch_bev_mask = True       # the literal per-camera loops
         rebatch = sca(q, k, k, None, bev_mask=mask, **kw)
+        sca.rebatch_bev_mask = False      # device-side mask fold + fused kernel
+        folded = sca(q, k, k, None, bev_mask=mask, **kw)
+    # (the camera-resident kernel adds the cameras' contributions in no fixed
+    # order: last-bit differences between two runs are expected)
+    assert (folded - fused).abs().max().item() <= 2e-6
     assert (fused - rebatch).abs().max().item() <= ATOL
     np.testing.assert_allclose(rebatch.cpu().numpy(), g["sca_out"], rtol=0,
                                atol=ATOL)
@@ -177,6 +183,56 @@ def test_backward_projection_vs_reference_golden(case):
     vis = g["per_cam_mask"]
     np.testing.assert_allclose(ref_cam.cpu().numpy()[vis],
                                g["reference_points_cam"][vis], atol=1e-4)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("which", ["a", "b"])
+@pytest.mark.parametrize("rebatch", [False, True])
+def test_backward_projection_bev_mask_vs_reference_golden(case, which, rebatch):
+    """``bev_mask`` (spatial_cross_attention_depth.py:156-169): outputs of the
+    reference's own BackwardProjection with (a) a random half of the BEV cells
+    masked and (b) a mask that empties camera 0's list, which triggers the
+    reference's empty-camera rule (:166-167: the camera's first visible query
+    is processed although masked, and not counted, :213-214).  The default
+    route folds the mask on the device (``fbbev_bev_mask_fold``) and runs the
+    fused kernels without any host synchronisation; ``rebatch`` runs the
+    reference-shaped loops."""
+    g, bp = build_bp(case, DEV)
+    sca = bp.transformer.encoder.layers[0].attentions[1]
+    sca.rebatch_bev_mask = rebatch
+    n_lvl = len(g["level_shapes"])
+    mlvl = [t(g[f"feat{i}"]) for i in range(n_lvl)]
+    bev_h, bev_w = int(g["bev_h"]), int(g["bev_w"])
+    mask = t(g[f"bev_mask_{which}"]).view(-1, bev_h, bev_w)
+    with torch.no_grad():
+        out = bp(mlvl, None, lss_bev=t(g["lss_bev"]),
+                 cam_params=cam_params(g, DEV), pred_img_depth=t(g["depth"]),
+                 bev_mask=mask)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"out_bev_mask_{which}"],
+                               rtol=0, atol=ATOL)
+
+
+def test_bev_mask_fold_encoding():
+    """fbbev_bev_mask_fold against its definition: 1 where mask & bev_mask;
+    a (camera, sample) pair left without any query gets 2 on the anchors of the
+    first query it sees at all; pairs that see nothing stay empty."""
+    from fbbev_b200.ops.ms_deform_attn import bev_mask_fold
+    gen = torch.Generator().manual_seed(5)
+    n_cams, bs, nq, Z = 5, 3, 1000, 4
+    mask = torch.rand(n_cams, bs, nq, Z, generator=gen) > 0.7
+    mask[3, 1] = False                          # camera 3 of sample 1: blind
+    bev = torch.rand(bs, nq, generator=gen) > 0.5
+    bev[2] &= ~mask[1, 2].any(-1)               # camera 1 of sample 2: emptied
+    bev[0] = False                              # every camera of sample 0
+    got = bev_mask_fold(mask.to(DEV), bev.to(DEV)).cpu()
+    want = (mask & bev[None, :, :, None]).to(torch.uint8)
+    for n in range(n_cams):
+        for b in range(bs):
+            if not want[n, b].any() and mask[n, b].any():
+                q0 = int(mask[n, b].any(-1).nonzero()[0])
+                want[n, b, q0] = mask[n, b, q0].to(torch.uint8) * 2
+    assert torch.equal(got, want)
+    assert (got == 2).any() and not got[3, 1].any()
 
 
 def _bp_module(bev, E, levels, input_size, B, points=8, dbound=(2.0, 42.0, 0.5),

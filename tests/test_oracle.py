@@ -321,3 +321,84 @@ def test_eager_prepare_restatement_vs_golden(case):
                                         rf, rb, (B, Z, Y, X, C))
     np.testing.assert_allclose(out.permute(0, 1, 3, 4, 2).numpy(),
                                g["bev_feat"], rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# BEVDet-lineage callers and the depth-net tail
+# ---------------------------------------------------------------------------
+def _lineage_inputs(g):
+    """depth_net output and frustum coordinates of a l_lss_* fixture, formed
+    on CPU with the golden's weights (the 1x1 conv is the step before the
+    path) and the reference's geometry chain (pinned by the f_* goldens)."""
+    import torch
+    from fbbev_b200.view_transformation.bevdet_lineage import \
+        LSSViewTransformer
+    grid = dict(x=list(g["grid_x"]), y=list(g["grid_y"]), z=list(g["grid_z"]),
+                depth=list(g["grid_depth"]))
+    vt = LSSViewTransformer(grid, tuple(int(v) for v in g["input_size"]),
+                            int(g["downsample"]),
+                            in_channels=int(g["in_channels"]),
+                            out_channels=int(g["out_channels"]))
+    cam = [torch.from_numpy(g[k]) for k in
+           ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")]
+    coor = vt.get_lidar_coor(*cam).numpy()
+    outs = []
+    for key, rec in (("x", "net_out"), ("x2", "net_out2")):
+        if rec in g:
+            outs.append(g[rec])
+            continue
+        x = torch.from_numpy(g[key])
+        B, N, Cin, H, W = x.shape
+        w = torch.from_numpy(g["depth_net.weight"])
+        b = torch.from_numpy(g["depth_net.bias"])
+        outs.append(torch.nn.functional.conv2d(
+            x.view(B * N, Cin, H, W), w, b).numpy())
+    B, N = g["x"].shape[:2]
+    H, W = g["x"].shape[-2:]
+    outs = [o.reshape(B, N, -1, H, W) for o in outs]
+    return vt, coor, outs
+
+
+@pytest.mark.parametrize("case,thresh", [("l_lss_v1", None),
+                                         ("l_lss_v2", 0.01),
+                                         ("l_lss_bevdepth", 0.01)])
+def test_lineage_oracle_vs_reference_golden(oracle_cpu, case, thresh):
+    """oracle.lift_ref (softmax + NHWC + thresholded index + pooling) against
+    the outputs of the reference's own LSSViewTransformer / LSSViewTransformer2
+    / LSSViewTransformerBEVDepth (necks/view_transformer.py), accelerate off
+    and on, first and second call."""
+    from oracle import lift_ref
+    g = load_golden(case)
+    vt, coor, (o1, o2) = _lineage_inputs(g)
+    lo, iv, gs = (vt.grid_lower_bound.numpy(), vt.grid_interval.numpy(),
+                  vt.grid_size.numpy())
+    D, C = vt.D, int(g["out_channels"])
+    bev, depth = lift_ref.lss_forward(o1, coor, lo, iv, gs, D, C, thresh)
+    np.testing.assert_allclose(depth, g["depth_plain"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(bev, g["bev_plain"], rtol=0, atol=1e-5)
+    bev_a, _ = lift_ref.lss_forward(o1, coor, lo, iv, gs, D, C, thresh, True)
+    np.testing.assert_allclose(bev_a, g["bev_acc"], rtol=0, atol=1e-5)
+    bev_b, _ = lift_ref.lss_forward(o2, coor, lo, iv, gs, D, C, thresh, True)
+    np.testing.assert_allclose(bev_b, g["bev_acc_second"], rtol=0, atol=1e-5)
+    if thresh is not None:     # the threshold must actually bite in the fixture
+        assert float(g["frac_below_thresh"]) > 0.02
+        full, _ = lift_ref.lss_forward(o1, coor, lo, iv, gs, D, C, None)
+        assert np.abs(full - bev).max() > 1e-4
+
+
+def test_cm_depth_net_tail_oracle_vs_reference_golden():
+    """oracle.lift_ref.lift_tail on the captured inputs of CM_DepthNet's tail
+    (depth_net.py:346-363) == the reference's returned (context, depth)."""
+    import torch
+    from oracle import lift_ref
+    g = load_golden("l_cm_tail")
+    ctx = torch.nn.functional.conv2d(
+        torch.from_numpy(g["ctx_in"]), torch.from_numpy(g["context_conv_weight"]),
+        torch.from_numpy(g["context_conv_bias"])).numpy()
+    depth, feat = lift_ref.lift_tail(g["logits"], ctx)
+    B, N = int(g["B"]), int(g["N"])
+    np.testing.assert_allclose(depth.reshape(g["depth"].shape), g["depth"],
+                               rtol=0, atol=1e-6)
+    np.testing.assert_allclose(
+        feat.reshape(B, N, *feat.shape[1:]),
+        g["context"].transpose(0, 1, 3, 4, 2), rtol=0, atol=1e-6)
