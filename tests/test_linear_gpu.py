@@ -147,3 +147,65 @@ def test_linear_pair_adds_position_in_loader(m, k):
             assert torch.equal(ya, za) and torch.equal(yb, zb)
     invalidate(wa)          # explicit cache-invalidation hook (EMA-style updates)
     assert not hasattr(wa, "_fbbev_packed")
+
+
+FFN_CASES = [
+    # m, embed, hidden, bias, residual, ln
+    (128, 80, 320, True, True, True),
+    (40000, 80, 320, True, True, True),      # the FB-OCC encoder layer
+    (1000, 80, 160, True, True, True),
+    (333, 64, 240, True, True, True),
+    (37, 80, 80, False, False, False),
+    (4097, 48, 400, True, False, True),
+    (271, 80, 320, True, True, False),
+]
+
+
+@pytest.mark.parametrize("m,e,h,bias,res,ln", FFN_CASES)
+def test_ffn_fused_matches_fp64(m, e, h, bias, res, ln):
+    """fbbev_ffn_fwd: LN(residual + relu(x W1^T + b1) W2^T + b2) in ONE kernel
+    (hidden tile in TMEM / shared memory only) against float64 torch, and
+    against the three-launch route it replaces."""
+    from fbbev_b200.ops.linear import ffn_fused, ffn_supported, linear_fused
+    g = torch.Generator(device="cuda").manual_seed(m + e + h)
+    dev = "cuda"
+    x = torch.randn(m, e, device=dev, generator=g)
+    w1 = torch.randn(h, e, device=dev, generator=g) / e ** 0.5
+    w2 = torch.randn(e, h, device=dev, generator=g) / h ** 0.5
+    b1 = torch.randn(h, device=dev, generator=g) if bias else None
+    b2 = torch.randn(e, device=dev, generator=g) if bias else None
+    r = x if res else None
+    lnp = (torch.rand(e, device=dev, generator=g) + 0.5,
+           torch.randn(e, device=dev, generator=g)) if ln else None
+    with torch.no_grad():
+        assert ffn_supported(x, w1, w2)
+        y = ffn_fused(x, w1, b1, w2, b2, residual=r,
+                      ln_weight=lnp[0] if ln else None,
+                      ln_bias=lnp[1] if ln else None, eps=1e-5)
+        hid = linear_fused(x, w1, b1, relu=True)
+        y3 = linear_fused(hid, w2, b2, residual=r,
+                          ln_weight=lnp[0] if ln else None,
+                          ln_bias=lnp[1] if ln else None, eps=1e-5)
+    hid64 = F.linear(x.double(), w1.double(),
+                     None if b1 is None else b1.double()).relu()
+    ref = _ref(hid64, w2, b2, False, r, lnp, 1e-5)
+    assert y.shape == (m, e)
+    err = (y.double() - ref).abs().max().item()
+    assert err < 3e-5, err
+    assert (y - y3).abs().max().item() < 3e-5
+    # a second call on the cached packs, other rows
+    with torch.no_grad():
+        y2 = ffn_fused(x.flip(0).contiguous(), w1, b1, w2, b2,
+                       residual=x.flip(0).contiguous() if res else None,
+                       ln_weight=lnp[0] if ln else None,
+                       ln_bias=lnp[1] if ln else None, eps=1e-5)
+    assert (y2.flip(0) - y).abs().max().item() < 1e-6
+
+
+def test_ffn_unsupported_shapes_are_refused():
+    from fbbev_b200 import _lib
+    L = _lib.lib()
+    assert L.fbbev_ffn_supported(80, 320) == 1
+    assert L.fbbev_ffn_supported(256, 1024) == 0     # configs[3]: per-Linear route
+    assert L.fbbev_ffn_supported(80, 300) == 0
+    assert L.fbbev_ffn_supported(80, 480) == 0
