@@ -440,6 +440,13 @@ def _call_key(name, a, ctx):
         tag = ", x+pos" if a[2] is not None else ""
         return (f"linear_tf32 {m}x{k}->{n} (two outputs{tag})",
                 4 * (m * k + add + k * n + m * n))
+    if name == "fbbev_ffn_fwd":
+        m, e, h = a[10], a[11], a[12]
+        res = m * e if a[6] is not None else 0
+        # x in, y out, residual, both weight matrices (the hidden m x h tile
+        # never leaves the SM)
+        return (f"ffn_tf32 {m}x{e}->{h}->{e}+res+ln",
+                4 * (2 * m * e + res + 2 * e * h))
     if name == "fbbev_msda_fused_fwd":
         bs, n_value, heads, ch, levels, nq, points = a[6:13]
         E = heads * ch

@@ -6,32 +6,39 @@
 // `norm` that follows it in the reference's operation order
 // (bevformer_encoder.py:251-377, config ffn_cfgs / operation_order).  The
 // reference runs two cuBLAS GEMMs, three element-wise kernels and a LayerNorm
-// kernel; round 1 / 2 of this repository ran three launches of
+// kernel; rounds 1 / 2 of this repository ran three launches of
 // linear_tf32_kernel (80 -> 192 + ReLU, 80 -> 128 + ReLU, 320 -> 80 + residual +
 // LayerNorm) with the 40000 x 320 hidden activation (51 MB) written to and read
-// back from HBM / L2 in between.  Here the hidden tile never leaves the SM:
+// back from HBM / L2 in between.  Here the hidden tile never leaves TENSOR
+// MEMORY:
 //
 //   GEMM1   H[128 x hidden] = X[128 x E] . W1^T  in `hidden / 80` column chunks of
-//           80, accumulators in TMEM columns [0, hidden)
-//   convert the two epilogue groups read a 40-column K-block of H from TMEM
-//           (tcgen05.ld, lane == row), add b1, apply ReLU, split into hi / lo
-//           (3xTF32, see linear_tf32.cu) and write it into shared memory in the
-//           UMMA K-major core-matrix layout -- i.e. they act as the A-operand
-//           loaders of the second GEMM
-//   GEMM2   Y[128 x E] += Hblk . W2blk^T per K-block, accumulator in TMEM
-//           columns [hidden, hidden + E)
-//   finish  group 0: tcgen05.ld of Y, + b2 + residual, LayerNorm, row-wise TMA
-//           bulk store (as the LayerNorm epilogue of linear_tf32_kernel)
+//           80 (A and B from shared memory), accumulators in TMEM columns
+//           [0, hidden)
+//   convert warps 8-11: tcgen05.ld a 40-column K-block of H (lane == row), add
+//           b1, ReLU, split into hi / lo (3xTF32, see linear_tf32.cu); hi goes
+//           back IN PLACE with tcgen05.st, lo into a two-stage ring of 40 TMEM
+//           columns.  An fp32 accumulator tile (lane == row, column == n) is
+//           already the layout tcgen05.mma wants for an A operand in tensor
+//           memory (lane == row, column == k), so the second GEMM reads its A
+//           operand where the first one left it: no shared-memory round trip
+//   GEMM2   Y[128 x E] += H_kb . W2_kb^T per K-block, A from TMEM, B from shared
+//           memory, accumulator in TMEM columns [hidden, hidden + E)
+//   finish  warps 0-3: tcgen05.ld of Y, + b2 + residual, LayerNorm, row-wise TMA
+//           bulk store (as the LayerNorm epilogue of linear_tf32_kernel), while
+//           the tensor pipe is already on the next tile
 //
-// Roles (14 warps): warps 0-3 / 8-11 epilogue groups 0 / 1 (group g converts
-// the K-blocks of parity g), warps 4-7 X loaders, warp 12 MMA issue + TMEM
-// allocation, warp 13 weight producer (one 1-D bulk copy per 25.6 KB stage:
-// W1 chunk x K-block, then W2 K-blocks, in the order the MMA warp consumes them).
-// Shared memory: X tile hi / lo (2 K-blocks, 80 KB) | hidden K-block ring (2 x
-// 40 KB, stage g owned by group g; stage 0 doubles as the LayerNorm slab) |
-// weight ring (2 - 3 stages) | barriers, biases, LayerNorm parameters.
+// Roles (14 warps): 0-3 finish, 4-7 loaders (X through registers; the weight
+// stages -- W1 chunk x K-block, then W2 K-blocks, 25.6 KB each, in the order the
+// MMA warp consumes them -- with 16-byte cp.async completing on mbarriers), 8-11
+// convert, 12 MMA issue (one elected lane) + TMEM allocation, 13 idle.  The
+// weights are streamed from L2 once per tile -- 410 KB -- which is why the ring is
+// as deep as shared memory allows and why a CTA takes whole tiles only.
+// Shared memory: X tile hi / lo (80 KB) | LayerNorm slab (42 KB) | weight ring
+// (4 x 25.6 KB) | barriers, biases, LayerNorm parameters.
+// TMEM columns: H [0, hidden) | Y [hidden, hidden + pad16(E)) | lo ring 2 x 40.
 //
-// Shapes: E <= 80, E % 4 == 0; hidden % 80 == 0, hidden + pad16(E) <= 512.
+// Shapes: E <= 80, E % 4 == 0; hidden % 80 == 0, hidden + pad16(E) + 80 <= 512.
 #include "common.cuh"
 #include "tc5.cuh"
 
@@ -47,10 +54,31 @@ constexpr int kAChunkStride = (kTileM / 8) * 128;   // bytes between K chunks
 constexpr int kThreads = 448;
 constexpr int kHC = 80;                 // hidden columns per GEMM1 chunk
 constexpr int kMaxE = 80;
-constexpr int kMaxHidden = 400;
+constexpr int kMaxHidden = 320;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 232448 - 1024;
 constexpr int kCtrlBytes = 512 + (kMaxHidden + 3 * kMaxE) * 4;
+constexpr int kSlabBytes = kTileM * (kMaxE + 4) * 4;
+
+#ifdef FFN_TRACE
+// timeline of CTA 0: every tracing thread (one per role) appends (tag, clock)
+// to its own region of a global buffer (plain stores, private counter)
+constexpr int kTraceCap = 200;
+__device__ long long g_ffn_trace[5 * 2 * kTraceCap];
+__device__ int g_ffn_trace_cnt[5];
+#define FTRACE_DECL int trn_ = 0;
+#define FTRACE_L(lane_, tag)                                                 \
+  do {                                                                       \
+    if (blockIdx.x == 0 && trn_ < kTraceCap) {                               \
+      g_ffn_trace[(lane_) * 2 * kTraceCap + 2 * trn_] = (tag);               \
+      g_ffn_trace[(lane_) * 2 * kTraceCap + 2 * trn_ + 1] = clock64();       \
+      g_ffn_trace_cnt[lane_] = ++trn_;                                       \
+    }                                                                        \
+  } while (0)
+#else
+#define FTRACE_DECL
+#define FTRACE_L(lane_, tag) do {} while (0)
+#endif
 
 struct Params {
   const float* x;         // [M][E]
@@ -69,14 +97,15 @@ struct Params {
 
 __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  FTRACE_DECL
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npad = p.npad, S = p.wstages;
   const uint32_t w1_stage = 2u * kHC * kKB * 4;           // W1 chunk x K-block
   const uint32_t w2_stage = 2u * (uint32_t)npad * kKB * 4;  // W2 K-block
   const uint32_t wstage = w1_stage > w2_stage ? w1_stage : w2_stage;
   unsigned char* xa = smem;                               // [n_kb1 <= 2] K-blocks
-  unsigned char* ha = smem + 2 * kABlock;                 // [2] K-blocks
-  unsigned char* wr = ha + 2 * kABlock;                   // [S] weight stages
+  unsigned char* slab_raw = smem + 2 * kABlock;           // [128][E + 4] floats
+  unsigned char* wr = slab_raw + kSlabBytes;              // [S] weight stages
   unsigned char* ctrl = wr + (size_t)S * wstage;
   const uint32_t bars = smem_u32(ctrl);
   const uint32_t bar_xfull = bars, bar_xempty = bars + 8;
@@ -91,8 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
   float* s_b2 = s_b1 + kMaxHidden;
   float* s_gamma = s_b2 + kMaxE;
   float* s_beta = s_gamma + kMaxE;
-  const uint32_t xa_base = smem_u32(xa), ha_base = smem_u32(ha),
-                 wr_base = smem_u32(wr);
+  const uint32_t xa_base = smem_u32(xa), wr_base = smem_u32(wr);
 
   if (warp == 12) {
     if (lane == 0) {
@@ -106,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       }
       for (int c = 0; c < p.n_hc; ++c) mbar_init(bar_hfull + 8u * c, 1);
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_wfull + 8u * s, 1);
+        mbar_init(bar_wfull + 8u * s, 128);   // cp.async arrivals of the loaders
         mbar_init(bar_wempty + 8u * s, 1);
       }
       fence_mbar_init();
@@ -131,17 +159,26 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FTRACE_L(4, 1);
   const int row_begin = blockIdx.x * p.rows_per_cta;
   const int row_end = min(p.M, row_begin + p.rows_per_cta);
   const int n_my = row_end > row_begin ? (row_end - row_begin + kTileM - 1) / kTileM : 0;
   const int stages_per_tile = p.n_hc * p.n_kb1 + p.n_kb2;
 
   if (warp >= 4 && warp < 8) {
-    // ============================== X loaders ================================
-    // the whole K range of a 128-row tile (n_kb1 <= 2 K-blocks) per round
+    // ========================= X and weight loaders ==========================
+    // Weights: every stage (25.6 KB, already in the operand layout) is copied
+    // with 16-byte cp.async by these 128 threads -- ~12 per thread and stage --
+    // and completes on the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so
+    // the warps run ahead by the depth of the ring.  (One elected thread issuing
+    // 1-D bulk copies was measured at ~35 GB/s per SM: 0.72 us per stage, the
+    // period of the whole kernel.)  X: the whole K range of a 128-row tile per
+    // round, through registers (hi / lo split).
     const int lw = warp - 4;
     const int r_lo = lane & 15, c_lo = lane >> 4;
-    for (int ti = 0; ti < n_my; ++ti) {
+    const int tid = threadIdx.x - 128;
+    uint32_t it = 0;
+    auto load_x = [&](int ti) {
       float4 v[2][10];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -160,7 +197,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (threadIdx.x == 128) FTRACE_L(0, 100 + ti);
       mbar_wait(bar_xempty, (ti & 1) ^ 1);   // GEMM1 of the previous tile done
+      if (threadIdx.x == 128) FTRACE_L(0, 110 + ti);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (u >= p.n_kb1) break;
@@ -186,33 +225,43 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       }
       fence_proxy_async();
       mbar_arrive(bar_xfull);
-    }
-  } else if (warp == 13) {
-    // ============================ weight producer ============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int ti = 0; ti < n_my; ++ti) {
-        for (int j = 0; j < stages_per_tile; ++j, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1u;
-          const float* src;
-          uint32_t bytes;
-          if (j < p.n_hc * p.n_kb1) {   // W1: chunk c, K-block kb
-            src = p.w1p + (size_t)j * (w1_stage / 4u);
-            bytes = w1_stage;
-          } else {                      // W2: K-block j - n_hc * n_kb1
-            src = p.w2p + (size_t)(j - p.n_hc * p.n_kb1) * (w2_stage / 4u);
-            bytes = w2_stage;
-          }
-          mbar_wait(bar_wempty + 8u * s, ph ^ 1u);
-          mbar_arrive_expect_tx(bar_wfull + 8u * s, bytes);
-          bulk_g2s(wr_base + s * wstage, src, bytes, bar_wfull + 8u * s);
+      if (threadIdx.x == 128) FTRACE_L(0, 120 + ti);
+    };
+    const int n_w1 = p.n_hc * p.n_kb1;
+    // the next tile's X goes in once GEMM1 of this tile is certainly through
+    const int x_point = min(stages_per_tile - 1, n_w1 + 2);
+    if (n_my > 0) load_x(0);
+    for (int ti = 0; ti < n_my; ++ti) {
+      for (int j = 0; j < stages_per_tile; ++j, ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1u;
+        const char* src;
+        uint32_t bytes;
+        if (j < n_w1) {   // W1: chunk c, K-block kb (j = c * n_kb1 + kb)
+          src = reinterpret_cast<const char*>(p.w1p) + (size_t)j * w1_stage;
+          bytes = w1_stage;
+        } else {          // W2: K-block j - n_w1
+          src = reinterpret_cast<const char*>(p.w2p) + (size_t)(j - n_w1) * w2_stage;
+          bytes = w2_stage;
         }
+        mbar_wait(bar_wempty + 8u * s, ph ^ 1u);
+        if (threadIdx.x == 128) FTRACE_L(1, 1000 + it);
+        const uint32_t dst = wr_base + s * wstage;
+        for (uint32_t o = (uint32_t)tid * 16u; o < bytes; o += 128u * 16u)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o),
+                       "l"(src + o)
+                       : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                         bar_wfull + 8u * s)
+                     : "memory");
+        if (j == x_point && ti + 1 < n_my) load_x(ti + 1);
       }
     }
-    __syncwarp();
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 12) {
     // =============================== MMA issue ===============================
-    if (lane == 0) {
+    // the whole warp walks the loop (all lanes poll the barriers); one elected
+    // lane issues -- see elect_one() for why not `if (lane == 0)`
+    {
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128
       const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) |
                               ((uint32_t)(kHC >> 3) << 17) | (8u << 24);
@@ -222,21 +271,27 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       const uint32_t w1_part = (uint32_t)kHC * kKB * 4;
       const uint32_t w2_part = (uint32_t)npad * kKB * 4;
       const uint32_t d_y = tmem_base + (uint32_t)p.hidden;
+      const uint32_t d_lo = d_y + (uint32_t)npad;
       uint32_t it = 0, hu = 0;   // weight stage counter, hidden K-block counter
       for (int ti = 0; ti < n_my; ++ti) {
+        if (lane == 0) FTRACE_L(2, 200 + ti);
         mbar_wait(bar_xfull, ti & 1);
         tc_fence_after();
+        if (lane == 0) FTRACE_L(2, 210 + ti);
         // ---- GEMM1: H chunk c = X . W1[80c : 80c + 80]^T ----
         for (int c = 0; c < p.n_hc; ++c) {
           const uint32_t d = tmem_base + (uint32_t)(c * kHC);
           for (int kb = 0; kb < p.n_kb1; ++kb, ++it) {
             const uint32_t s = it % S, ph = (it / S) & 1u;
             mbar_wait(bar_wfull + 8u * s, ph);
+            fence_proxy_async();   // cp.async (generic proxy) -> tcgen05 reads
             tc_fence_after();
+            if (lane == 0) FTRACE_L(2, 2000 + it);
             const uint32_t a_hi = xa_base + (uint32_t)kb * kABlock;
             const uint32_t a_lo = a_hi + kAPart;
             const uint32_t w_hi = wr_base + s * wstage;
             const uint32_t w_lo = w_hi + w1_part;
+            if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kChunks / 2; ++k) {
               const uint32_t ao = 2u * k * kAChunkStride, bo = 2u * k * lbo_b1;
@@ -249,10 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
               mma_tf32(d, dah, dbl, idesc1, 1u);
             }
             tc_commit(bar_wempty + 8u * s);
+            if (kb == p.n_kb1 - 1) {
+              tc_commit(bar_hfull + 8u * c);    // chunk c can be converted
+              if (c == p.n_hc - 1) tc_commit(bar_xempty);   // X tile consumed
+            }
+            }
+            __syncwarp();
           }
-          tc_commit(bar_hfull + 8u * c);        // chunk c can be converted
         }
-        tc_commit(bar_xempty);                  // X tile consumed
         // ---- GEMM2: Y += Hblk . W2blk^T ----
         mbar_wait(bar_yempty, (ti & 1) ^ 1);    // Y of the previous tile drained
         tc_fence_after();
@@ -260,153 +319,160 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
           const uint32_t s = it % S, ph = (it / S) & 1u;
           const uint32_t g = (uint32_t)kb & 1u, hph = (hu >> 1) & 1u;
           mbar_wait(bar_wfull + 8u * s, ph);
+          fence_proxy_async();
+          if (lane == 0) FTRACE_L(2, 2000 + it);
           mbar_wait(bar_hafull + 8u * g, hph);
           tc_fence_after();
-          const uint32_t a_hi = ha_base + g * kABlock;
-          const uint32_t a_lo = a_hi + kAPart;
+          if (lane == 0) FTRACE_L(2, 3000 + it);
+          // A from tensor memory: hi where GEMM1 left the K-block (converted
+          // in place), lo in ring stage g
+          const uint32_t a_hi = tmem_base + (uint32_t)(kb * kKB);
+          const uint32_t a_lo = d_lo + g * (uint32_t)kKB;
           const uint32_t w_hi = wr_base + s * wstage;
           const uint32_t w_lo = w_hi + w2_part;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kChunks / 2; ++k) {
-            const uint32_t ao = 2u * k * kAChunkStride, bo = 2u * k * lbo_b2;
-            const uint64_t dah = smem_desc(a_hi + ao, kAChunkStride, 128);
-            const uint64_t dal = smem_desc(a_lo + ao, kAChunkStride, 128);
+            const uint32_t bo = 2u * k * lbo_b2;
             const uint64_t dbh = smem_desc(w_hi + bo, lbo_b2, 128);
             const uint64_t dbl = smem_desc(w_lo + bo, lbo_b2, 128);
-            mma_tf32(d_y, dah, dbh, idesc2, (kb | k) != 0);
-            mma_tf32(d_y, dal, dbh, idesc2, 1u);
-            mma_tf32(d_y, dah, dbl, idesc2, 1u);
+            mma_tf32_ts(d_y, a_hi + 8u * k, dbh, idesc2, (kb | k) != 0);
+            mma_tf32_ts(d_y, a_lo + 8u * k, dbh, idesc2, 1u);
+            mma_tf32_ts(d_y, a_hi + 8u * k, dbl, idesc2, 1u);
           }
           tc_commit(bar_wempty + 8u * s);
           tc_commit(bar_haempty + 8u * g);
+          if (kb == p.n_kb2 - 1) tc_commit(bar_yfull);
+          }
+          __syncwarp();
         }
-        tc_commit(bar_yfull);
+        if (lane == 0) FTRACE_L(2, 220 + ti);
       }
     }
     __syncwarp();
-  } else {
-    // ======================= convert (+ finish, group 0) =====================
-    const uint32_t grp = warp >> 3;          // 0: warps 0-3, 1: warps 8-11
+  } else if (warp != 13) {
+    // ===================== convert (warps 8-11) / finish (0-3) ===============
+    const uint32_t grp = warp >> 3;          // 0: finish, 1: convert
     const int q = warp & 3;
     const int gt = q * 32 + lane;            // row of the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int bar_id = 1 + (int)grp;
-    auto group_sync = [&]() {
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    };
     const int E = p.E;
-    float* slab = reinterpret_cast<float*>(ha);          // [128][E], group 0 only
-    float* my_row = slab + (size_t)gt * E;
-    unsigned char* my_ha = ha + (size_t)grp * kABlock;
-    const uint32_t row_off = (uint32_t)(gt >> 3) * 128u + (uint32_t)(gt & 7) * 16u;
-    const int kb_per_chunk = kHC / kKB;      // 2
-    uint32_t use = 0;                        // uses of this group's ha stage
-    for (int ti = 0; ti < n_my; ++ti) {
-      const int row0 = row_begin + ti * kTileM;
-      if (grp == 0) {
-        bulk_wait_read0();   // my row of the previous tile has left the slab
-        group_sync();        // ... and so have all the others
-      }
-      // ---- convert this group's K-blocks: kb = 2 j + grp, j = 0 .. n_kb2/2 ----
-      for (int kb = (int)grp; kb < p.n_kb2; kb += 2, ++use) {
-        const int c = kb / kb_per_chunk;
-        mbar_wait(bar_hfull + 8u * c, ti & 1);
-        mbar_wait(bar_haempty + 8u * grp, (use & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t taddr = lane_base + (uint32_t)(kb * kKB);
-        float v[kKB];
-        tmem_ld16(taddr, v);
-        tmem_ld16(taddr + 16u, v + 16);
-        tmem_ld8(taddr + 32u, v + 32);
-        tmem_ld_wait();
-        const float4* bias4 = reinterpret_cast<const float4*>(s_b1 + kb * kKB);
+    if (grp == 1) {
+      const uint32_t t_lo = lane_base + (uint32_t)(p.hidden + npad);
+      uint32_t use = 0;                      // K-blocks converted so far
+      for (int ti = 0; ti < n_my; ++ti) {
+        for (int kb = 0; kb < p.n_kb2; ++kb, ++use) {
+          const uint32_t g = use & 1u;       // == kb & 1 (n_kb2 is even)
+          mbar_wait(bar_hfull + 8u * (kb / (kHC / kKB)), ti & 1);
+          if (threadIdx.x == 256) FTRACE_L(3, 4000 + use);
+          mbar_wait(bar_haempty + 8u * g, ((use >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (threadIdx.x == 256) FTRACE_L(3, 5000 + use);
+          const uint32_t taddr = lane_base + (uint32_t)(kb * kKB);
+          float v[kKB], lo[kKB];
+          tmem_ld16(taddr, v);
+          tmem_ld16(taddr + 16u, v + 16);
+          tmem_ld8(taddr + 32u, v + 32);
+          tmem_ld_wait();
+          const float* bias = s_b1 + kb * kKB;
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          const float4 bb = bias4[ch];
-          float4 t = make_float4(fmaxf(v[4 * ch] + bb.x, 0.f),
-                                 fmaxf(v[4 * ch + 1] + bb.y, 0.f),
-                                 fmaxf(v[4 * ch + 2] + bb.z, 0.f),
-                                 fmaxf(v[4 * ch + 3] + bb.w, 0.f));
-          float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(t.x) & 0xFFFFE000u);
-          hi.y = __uint_as_float(__float_as_uint(t.y) & 0xFFFFE000u);
-          hi.z = __uint_as_float(__float_as_uint(t.z) & 0xFFFFE000u);
-          hi.w = __uint_as_float(__float_as_uint(t.w) & 0xFFFFE000u);
-          lo.x = t.x - hi.x; lo.y = t.y - hi.y;
-          lo.z = t.z - hi.z; lo.w = t.w - hi.w;
-          unsigned char* a = my_ha + (uint32_t)ch * kAChunkStride + row_off;
-          *reinterpret_cast<float4*>(a) = hi;
-          *reinterpret_cast<float4*>(a + kAPart) = lo;
+          for (int c = 0; c < kKB; ++c) {
+            const float t = fmaxf(v[c] + bias[c], 0.f);
+            const float hi = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);
+            v[c] = hi;
+            lo[c] = t - hi;
+          }
+          tmem_st16(taddr, v);
+          tmem_st16(taddr + 16u, v + 16);
+          tmem_st8(taddr + 32u, v + 32);
+          const uint32_t tl = t_lo + g * (uint32_t)kKB;
+          tmem_st16(tl, lo);
+          tmem_st16(tl + 16u, lo + 16);
+          tmem_st8(tl + 32u, lo + 32);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_hafull + 8u * g);
+          if (threadIdx.x == 256) FTRACE_L(3, 6000 + use);
         }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(bar_hafull + 8u * grp);
       }
-      if (grp != 0) continue;
+    } else {
       // ---- finish: Y + b2 + residual -> LayerNorm -> bulk store ----
-      mbar_wait(bar_yfull, ti & 1);
-      tc_fence_after();
+      const int pitch = E + 4;
+      float* slab = reinterpret_cast<float*>(slab_raw);
+      float* my_row = slab + (size_t)gt * pitch;
       const uint32_t ty = lane_base + (uint32_t)p.hidden;
       const int nc16 = npad >> 4;
-      const bool in_range = row0 + gt < row_end;
-      const float* res = (p.residual && in_range)
-                             ? p.residual + (size_t)(row0 + gt) * p.ldr
-                             : nullptr;
-      float sum = 0.f, sq = 0.f, shiftK = 0.f;
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int row0 = row_begin + ti * kTileM;
+        const bool in_range = row0 + gt < row_end;
+        const float* res = (p.residual && in_range)
+                               ? p.residual + (size_t)(row0 + gt) * p.ldr
+                               : nullptr;
+        bulk_wait_read0();   // my row of the previous tile has left the slab
+        if (threadIdx.x == 0) FTRACE_L(4, 300 + ti);
+        mbar_wait(bar_yfull, ti & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0) FTRACE_L(4, 310 + ti);
+        float sum = 0.f, sq = 0.f, shiftK = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < nc16; ++c) {
-        float v[16];
-        tmem_ld16(ty + 16u * c, v);
-        tmem_ld_wait();
-        if (c == nc16 - 1) {
-          tc_fence_before();
-          mbar_arrive(bar_yempty);
-        }
+        for (int c = 0; c < nc16; ++c) {
+          float v[16];
+          tmem_ld16(ty + 16u * c, v);
+          tmem_ld_wait();
+          if (c == nc16 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_yempty);
+          }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = 16 * c + 4 * j;
-          if (col < E) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_b2 + col);
-            float4 t = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y,
-                                   v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
-            if (res) {
-              const float4 r = __ldg(reinterpret_cast<const float4*>(res + col));
-              t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+          for (int j = 0; j < 4; ++j) {
+            const int col = 16 * c + 4 * j;
+            if (col < E) {
+              const float4 bb = *reinterpret_cast<const float4*>(s_b2 + col);
+              float4 t = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y,
+                                     v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+              if (res) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(res + col));
+                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+              }
+              *reinterpret_cast<float4*>(my_row + col) = t;
+              if (col == 0) shiftK = t.x;
+              const float a = t.x - shiftK, b = t.y - shiftK, cc = t.z - shiftK,
+                          d = t.w - shiftK;
+              sum += (a + b) + (cc + d);
+              sq += (a * a + b * b) + (cc * cc + d * d);
             }
-            *reinterpret_cast<float4*>(my_row + col) = t;
-            if (col == 0) shiftK = t.x;
-            const float a = t.x - shiftK, b = t.y - shiftK, cc = t.z - shiftK,
-                        d = t.w - shiftK;
-            sum += (a + b) + (cc + d);
-            sq += (a * a + b * b) + (cc * cc + d * d);
           }
         }
-      }
-      if (p.gamma) {
-        const float dm = sum / (float)E;
-        const float mean = shiftK + dm;
-        const float var = fmaxf(sq / (float)E - dm * dm, 0.f);
-        const float rstd = rsqrtf(var + p.eps);
-        const float4* g4 = reinterpret_cast<const float4*>(s_gamma);
-        const float4* b4 = reinterpret_cast<const float4*>(s_beta);
+        if (p.gamma) {
+          const float dm = sum / (float)E;
+          const float mean = shiftK + dm;
+          const float var = fmaxf(sq / (float)E - dm * dm, 0.f);
+          const float rstd = rsqrtf(var + p.eps);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma);
+          const float4* b4 = reinterpret_cast<const float4*>(s_beta);
 #pragma unroll 4
-        for (int j = 0; j < (E >> 2); ++j) {
-          float4* cell = reinterpret_cast<float4*>(my_row + 4 * j);
-          const float4 t = *cell, g = g4[j], b = b4[j];
-          *cell = make_float4(fmaf((t.x - mean) * rstd, g.x, b.x),
-                              fmaf((t.y - mean) * rstd, g.y, b.y),
-                              fmaf((t.z - mean) * rstd, g.z, b.z),
-                              fmaf((t.w - mean) * rstd, g.w, b.w));
+          for (int j = 0; j < (E >> 2); ++j) {
+            float4* cell = reinterpret_cast<float4*>(my_row + 4 * j);
+            const float4 t = *cell, g = g4[j], b = b4[j];
+            *cell = make_float4(fmaf((t.x - mean) * rstd, g.x, b.x),
+                                fmaf((t.y - mean) * rstd, g.y, b.y),
+                                fmaf((t.z - mean) * rstd, g.z, b.z),
+                                fmaf((t.w - mean) * rstd, g.w, b.w));
+          }
         }
+        // the finished row leaves as ONE bulk (TMA) store issued by its own
+        // thread (its own STS are ordered before the copy by the proxy fence)
+        if (in_range) {
+          fence_proxy_async();
+          bulk_s2g(p.y + (size_t)(row0 + gt) * p.ldy, smem_u32(my_row),
+                   (uint32_t)E * 4u);
+        }
+        bulk_commit();
+        if (threadIdx.x == 0) FTRACE_L(4, 320 + ti);
       }
-      if (in_range) {
-        fence_proxy_async();
-        bulk_s2g(p.y + (size_t)(row0 + gt) * p.ldy, smem_u32(my_row),
-                 (uint32_t)E * 4u);
-      }
-      bulk_commit();
+      bulk_wait0();
+      if (threadIdx.x == 0) FTRACE_L(4, 330);
     }
-    if (grp == 0) bulk_wait0();
   }
 
   tc_fence_before();
@@ -427,10 +493,19 @@ static inline int pad16(int n) { return (n + 15) / 16 * 16; }
 
 using namespace fbbev;
 
+#ifdef FFN_TRACE
+FBBEV_API int fbbev_debug_ffn_trace(long long* out, int* counts) {
+  cudaMemcpyFromSymbol(counts, ffn::g_ffn_trace_cnt, sizeof(int) * 5);
+  cudaMemcpyFromSymbol(out, ffn::g_ffn_trace,
+                       sizeof(long long) * 5 * 2 * ffn::kTraceCap);
+  return ffn::kTraceCap;
+}
+#endif
+
 FBBEV_API int fbbev_ffn_supported(int32_t embed, int32_t hidden) {
   return embed > 0 && embed <= ffn::kMaxE && embed % 4 == 0 && hidden > 0 &&
                  hidden % ffn::kHC == 0 &&
-                 hidden + ffn::pad16(embed) <= ffn::kTmemCols &&
+                 hidden + ffn::pad16(embed) + 2 * ffn::kKB <= ffn::kTmemCols &&
                  hidden <= ffn::kMaxHidden
              ? 1
              : 0;
@@ -469,7 +544,8 @@ FBBEV_API int fbbev_ffn_fwd(const float* x, int64_t ldx, const float* w1_packed,
   const size_t w1_stage = 2 * (size_t)ffn::kHC * ffn::kKB * 4;
   const size_t w2_stage = 2 * (size_t)p.npad * ffn::kKB * 4;
   const size_t wstage = w1_stage > w2_stage ? w1_stage : w2_stage;
-  const size_t fixed = 4 * (size_t)ffn::kABlock + ffn::kCtrlBytes;
+  const size_t fixed =
+      2 * (size_t)ffn::kABlock + ffn::kSlabBytes + ffn::kCtrlBytes;
   int S = (int)((ffn::kSmemLimit - fixed) / wstage);
   S = S > 4 ? 4 : S;
   if (S < 2) return FBBEV_ERR_UNSUPPORTED;
@@ -482,10 +558,13 @@ FBBEV_API int fbbev_ffn_fwd(const float* x, int64_t ldx, const float* w1_packed,
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
+  // whole tiles per CTA: every tile costs one pass over the weights (410 KB
+  // from L2) whatever its row count, so 105 CTAs x 3 full tiles beat 148 CTAs
+  // x (2 full + 1 sliver) for 40000 rows: same makespan, 30 % less L2 traffic
   const int n_tiles = (int)ceil_div64(m, ffn::kTileM);
-  int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  p.rows_per_cta = (int)(ceil_div64(ceil_div64(m, grid), 8) * 8);
-  grid = (int)ceil_div64(m, p.rows_per_cta);
+  const int tiles_per_cta = (int)ceil_div64(n_tiles, n_sm);
+  p.rows_per_cta = tiles_per_cta * ffn::kTileM;
+  const int grid = (int)ceil_div64(m, p.rows_per_cta);
   static size_t allowed = 0;
   if (smem > allowed) {
     cudaError_t e = cudaFuncSetAttribute(

@@ -274,7 +274,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     __syncwarp();
   } else if (warp == 12) {
     // ================================ MMA issue ===============================
-    if (lane == 0) {
+    // The whole warp walks the loop (all lanes poll the barriers) and ONE
+    // elected lane issues: under a divergent `if (lane == 0)` the compiler
+    // wraps every UTCHMMA in an ELECT / BRA.U.ANY serialisation loop (see
+    // elect_one(), tc5.cuh) -- ~100 instead of ~52 cycles per MMA.
+    {
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = npad
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
                              ((uint32_t)(npad >> 3) << 17) | (8u << 24);
@@ -289,26 +293,29 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           const uint32_t s = it % S, ph = (it / S) & 1u;
           mbar_wait(bar_full + 8u * s, ph);
           tc_fence_after();
-          TRACE(2, 400 + it);
+          if (lane == 0) TRACE(2, 400 + it);
           const uint32_t a_hi = smem_base + s * stage_bytes;
           const uint32_t a_lo = a_hi + kAPart;
           const uint32_t w_hi = a_lo + kAPart;
           const uint32_t w_lo = w_hi + w_part;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kChunks / 2; ++k) {
-            const uint32_t ao = 2u * k * kAChunkStride, bo = 2u * k * lbo_b;
-            const uint64_t dah = smem_desc(a_hi + ao, kAChunkStride, 128);
-            const uint64_t dal = smem_desc(a_lo + ao, kAChunkStride, 128);
-            const uint64_t dbh = smem_desc(w_hi + bo, lbo_b, 128);
-            const uint64_t dbl = smem_desc(w_lo + bo, lbo_b, 128);
-            mma_tf32(d, dah, dbh, idesc, (kb | k) != 0);
-            mma_tf32(d, dal, dbh, idesc, 1u);
-            mma_tf32(d, dah, dbl, idesc, 1u);
+            for (int k = 0; k < kChunks / 2; ++k) {
+              const uint32_t ao = 2u * k * kAChunkStride, bo = 2u * k * lbo_b;
+              const uint64_t dah = smem_desc(a_hi + ao, kAChunkStride, 128);
+              const uint64_t dal = smem_desc(a_lo + ao, kAChunkStride, 128);
+              const uint64_t dbh = smem_desc(w_hi + bo, lbo_b, 128);
+              const uint64_t dbl = smem_desc(w_lo + bo, lbo_b, 128);
+              mma_tf32(d, dah, dbh, idesc, (kb | k) != 0);
+              mma_tf32(d, dal, dbh, idesc, 1u);
+              mma_tf32(d, dah, dbl, idesc, 1u);
+            }
+            tc_commit(bar_empty + 8u * s);
+            if (kb == p.n_kb - 1) tc_commit(bar_tfull + 8u * acc);
           }
-          tc_commit(bar_empty + 8u * s);
+          __syncwarp();
         }
-        tc_commit(bar_tfull + 8u * acc);
-        TRACE(2, 500 + tc);
+        if (lane == 0) TRACE(2, 500 + tc);
       }
     }
     __syncwarp();

@@ -237,6 +237,22 @@ class FFN(BaseModule):
         drops = [m for m in self.layers.modules() if isinstance(m, nn.Dropout)]
         if (_fused_linear_on(x, self.dropout_layer, *drops) and
                 all(isinstance(l[1], nn.ReLU) for l in self.layers[:-2])):
+            res = (identity if identity is not None else x) \
+                if self.add_identity else None
+            fc1, fc2 = self.layers[0][0], self.layers[-2]
+            if (self.num_fcs == 2 and
+                    os.environ.get('FBBEV_FFN_FUSED', '1') == '1' and
+                    _linear_ops.ffn_supported(x, fc1.weight, fc2.weight) and
+                    (post_norm is None or
+                     _linear_ops.ln_supported(fc2.weight.shape[0]))):
+                # both Linears, the ReLU, the identity add and the LayerNorm
+                # as one kernel: the hidden activation stays in tensor memory
+                return _linear_ops.ffn_fused(
+                    x, fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+                    residual=res,
+                    ln_weight=None if post_norm is None else post_norm.weight,
+                    ln_bias=None if post_norm is None else post_norm.bias,
+                    eps=1e-5 if post_norm is None else post_norm.eps)
             out = x
             for l in self.layers[:-2]:
                 out = _linear(l[0], out, relu=True)

@@ -156,7 +156,7 @@ FFN_CASES = [
     (1000, 80, 160, True, True, True),
     (333, 64, 240, True, True, True),
     (37, 80, 80, False, False, False),
-    (4097, 48, 400, True, False, True),
+    (4097, 48, 240, True, False, True),
     (271, 80, 320, True, True, False),
 ]
 
@@ -208,4 +208,4 @@ def test_ffn_unsupported_shapes_are_refused():
     assert L.fbbev_ffn_supported(80, 320) == 1
     assert L.fbbev_ffn_supported(256, 1024) == 0     # configs[3]: per-Linear route
     assert L.fbbev_ffn_supported(80, 300) == 0
-    assert L.fbbev_ffn_supported(80, 480) == 0
+    assert L.fbbev_ffn_supported(80, 400) == 0    # TMEM: H + Y + lo ring > 512
