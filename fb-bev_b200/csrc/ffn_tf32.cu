@@ -28,12 +28,17 @@
 //           bulk store (as the LayerNorm epilogue of linear_tf32_kernel), while
 //           the tensor pipe is already on the next tile
 //
-// Roles (14 warps): 0-3 finish, 4-7 loaders (X through registers; the weight
-// stages -- W1 chunk x K-block, then W2 K-blocks, 25.6 KB each, in the order the
-// MMA warp consumes them -- with 16-byte cp.async completing on mbarriers), 8-11
-// convert, 12 MMA issue (one elected lane) + TMEM allocation, 13 idle.  The
-// weights are streamed from L2 once per tile -- 410 KB -- which is why the ring is
-// as deep as shared memory allows and why a CTA takes whole tiles only.
+// Roles (14 warps): 0-3 finish, 4-7 X loaders, 8-11 convert, 12 MMA issue (one
+// elected lane) + TMEM allocation, 13 weight producer (one 1-D bulk copy per
+// 25.6 KB stage: W1 chunk x K-block, then W2 K-blocks, in the order the MMA warp
+// consumes them).  The weights do not fit beside the X tile, so they are streamed
+// from L2 once per tile -- 410 KB -- and that stream bounds the kernel: ~0.72 us
+// per stage against 0.40 us for the stage's 15 MMAs (tools/micro/mma_rate.cu:
+// 52 / 40 cycles per MMA with A in shared / tensor memory), whether one thread
+// issues bulk copies or 128 threads issue cp.async, and not improved by sending
+// the weights unsplit and splitting them on the SM (68 us instead of 52: the
+// split costs the loader warps more than the bytes saved; profiles/r02_notes.md).
+// Hence the ring as deep as shared memory allows, and whole tiles per CTA.
 // Shared memory: X tile hi / lo (80 KB) | LayerNorm slab (42 KB) | weight ring
 // (4 x 25.6 KB) | barriers, biases, LayerNorm parameters.
 // TMEM columns: H [0, hidden) | Y [hidden, hidden + pad16(E)) | lo ring 2 x 40.
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       }
       for (int c = 0; c < p.n_hc; ++c) mbar_init(bar_hfull + 8u * c, 1);
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_wfull + 8u * s, 128);   // cp.async arrivals of the loaders
+        mbar_init(bar_wfull + 8u * s, 1);     // expect_tx of the producer
         mbar_init(bar_wempty + 8u * s, 1);
       }
       fence_mbar_init();
@@ -166,18 +171,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
   const int stages_per_tile = p.n_hc * p.n_kb1 + p.n_kb2;
 
   if (warp >= 4 && warp < 8) {
-    // ========================= X and weight loaders ==========================
-    // Weights: every stage (25.6 KB, already in the operand layout) is copied
-    // with 16-byte cp.async by these 128 threads -- ~12 per thread and stage --
-    // and completes on the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so
-    // the warps run ahead by the depth of the ring.  (One elected thread issuing
-    // 1-D bulk copies was measured at ~35 GB/s per SM: 0.72 us per stage, the
-    // period of the whole kernel.)  X: the whole K range of a 128-row tile per
-    // round, through registers (hi / lo split).
+    // ============================== X loaders ================================
+    // the whole K range of a 128-row tile per round, through registers (hi / lo
+    // split)
     const int lw = warp - 4;
     const int r_lo = lane & 15, c_lo = lane >> 4;
-    const int tid = threadIdx.x - 128;
-    uint32_t it = 0;
     auto load_x = [&](int ti) {
       float4 v[2][10];
 #pragma unroll
@@ -227,36 +225,34 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       mbar_arrive(bar_xfull);
       if (threadIdx.x == 128) FTRACE_L(0, 120 + ti);
     };
+    for (int ti = 0; ti < n_my; ++ti) load_x(ti);
+  } else if (warp == 13) {
+    // ============================ weight producer ============================
+    // one 1-D bulk copy (TMA) per stage, issued by an elected lane as soon as
+    // the stage is free; all lanes walk the loop (see elect_one())
     const int n_w1 = p.n_hc * p.n_kb1;
-    // the next tile's X goes in once GEMM1 of this tile is certainly through
-    const int x_point = min(stages_per_tile - 1, n_w1 + 2);
-    if (n_my > 0) load_x(0);
+    uint32_t it = 0;
     for (int ti = 0; ti < n_my; ++ti) {
       for (int j = 0; j < stages_per_tile; ++j, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
-        const char* src;
+        const float* src;
         uint32_t bytes;
         if (j < n_w1) {   // W1: chunk c, K-block kb (j = c * n_kb1 + kb)
-          src = reinterpret_cast<const char*>(p.w1p) + (size_t)j * w1_stage;
+          src = p.w1p + (size_t)j * (w1_stage / 4u);
           bytes = w1_stage;
         } else {          // W2: K-block j - n_w1
-          src = reinterpret_cast<const char*>(p.w2p) + (size_t)(j - n_w1) * w2_stage;
+          src = p.w2p + (size_t)(j - n_w1) * (w2_stage / 4u);
           bytes = w2_stage;
         }
         mbar_wait(bar_wempty + 8u * s, ph ^ 1u);
-        if (threadIdx.x == 128) FTRACE_L(1, 1000 + it);
-        const uint32_t dst = wr_base + s * wstage;
-        for (uint32_t o = (uint32_t)tid * 16u; o < bytes; o += 128u * 16u)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o),
-                       "l"(src + o)
-                       : "memory");
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
-                         bar_wfull + 8u * s)
-                     : "memory");
-        if (j == x_point && ti + 1 < n_my) load_x(ti + 1);
+        if (lane == 0) FTRACE_L(1, 1000 + it);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_wfull + 8u * s, bytes);
+          bulk_g2s(wr_base + s * wstage, src, bytes, bar_wfull + 8u * s);
+        }
+        __syncwarp();
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 12) {
     // =============================== MMA issue ===============================
     // the whole warp walks the loop (all lanes poll the barriers); one elected
@@ -284,7 +280,6 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
           for (int kb = 0; kb < p.n_kb1; ++kb, ++it) {
             const uint32_t s = it % S, ph = (it / S) & 1u;
             mbar_wait(bar_wfull + 8u * s, ph);
-            fence_proxy_async();   // cp.async (generic proxy) -> tcgen05 reads
             tc_fence_after();
             if (lane == 0) FTRACE_L(2, 2000 + it);
             const uint32_t a_hi = xa_base + (uint32_t)kb * kABlock;
@@ -319,7 +314,6 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
           const uint32_t s = it % S, ph = (it / S) & 1u;
           const uint32_t g = (uint32_t)kb & 1u, hph = (hu >> 1) & 1u;
           mbar_wait(bar_wfull + 8u * s, ph);
-          fence_proxy_async();
           if (lane == 0) FTRACE_L(2, 2000 + it);
           mbar_wait(bar_hafull + 8u * g, hph);
           tc_fence_after();
