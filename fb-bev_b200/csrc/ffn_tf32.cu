@@ -399,14 +399,40 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
       for (int ti = 0; ti < n_my; ++ti) {
         const int row0 = row_begin + ti * kTileM;
         const bool in_range = row0 + gt < row_end;
-        const float* res = (p.residual && in_range)
-                               ? p.residual + (size_t)(row0 + gt) * p.ldr
-                               : nullptr;
         bulk_wait_read0();   // my row of the previous tile has left the slab
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // ... and everybody's
+        // residual rows of this tile -> slab with cp.async while the tensor
+        // pipe is still on the tile (4 lanes per row, 64 contiguous bytes per
+        // row and round: coalesced; a load per thread and row inside the pass
+        // below cost a full L2 round trip each: 6 us per tile)
+        if (p.residual) {
+          const int crow = gt >> 2, cq = gt & 3;
+#pragma unroll 1
+          for (int c = 0; c < nc16; ++c) {
+            const int col = 16 * c + 4 * cq;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = crow + 32 * i;
+              const bool ok = row0 + r < row_end && col < E;
+              const float* src = p.residual +
+                                 (size_t)(ok ? row0 + r : row_begin) * p.ldr +
+                                 (ok ? col : 0);
+              const uint32_t dst = smem_u32(slab + (size_t)r * pitch + col);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                           "l"(src), "r"(ok ? 16 : 0)
+                           : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (threadIdx.x == 0) FTRACE_L(4, 300 + ti);
         mbar_wait(bar_yfull, ti & 1);
         tc_fence_after();
         if (threadIdx.x == 0) FTRACE_L(4, 310 + ti);
+        if (p.residual) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         float sum = 0.f, sq = 0.f, shiftK = 0.f;
 #pragma unroll 1
         for (int c = 0; c < nc16; ++c) {
@@ -424,11 +450,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tf32_kernel(const Params p) {
               const float4 bb = *reinterpret_cast<const float4*>(s_b2 + col);
               float4 t = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y,
                                      v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
-              if (res) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(res + col));
+              float4* cell = reinterpret_cast<float4*>(my_row + col);
+              if (p.residual) {
+                const float4 r = *cell;
                 t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
               }
-              *reinterpret_cast<float4*>(my_row + col) = t;
+              *cell = t;
               if (col == 0) shiftK = t.x;
               const float a = t.x - shiftK, b = t.y - shiftK, cc = t.z - shiftK,
                           d = t.w - shiftK;

@@ -1,10 +1,11 @@
 """Row-wise Linear (+ bias, ReLU, residual, LayerNorm) on the tcgen05 tensor cores.
 
-Host side of ``fbbev_linear_fwd`` (include/fbbev_b200.h): the nn.Linear /
-LayerNorm / residual chain of the reference's encoder layer
+Host side of ``fbbev_linear_fwd`` / ``fbbev_ffn_fwd`` (include/fbbev_b200.h): the
+nn.Linear / LayerNorm / residual chain of the reference's encoder layer
 (bevformer_encoder.py:251-377, spatial_cross_attention_depth.py:219, 420-427)
-as one kernel per Linear.  Inference only (no autograd); the modules in
-``view_transformation/backward_projection.py`` use it when gradients are off.
+as one kernel per Linear (one for the whole FFN).  With autograd recording,
+:class:`LinearTF32Function` keeps the forward on the same kernel and forms the
+three gradient products with plain library GEMMs (cuBLAS through torch).
 """
 import torch
 
@@ -221,3 +222,55 @@ def ffn_fused(x, w1, b1, w2, b2, residual=None, ln_weight=None, ln_bias=None,
         m, embed, hidden, float(eps), _lib.ptr(y), y.stride(0),
         _lib.stream_ptr(x.device)), "fbbev_ffn_fwd")
     return y.view(*lead, embed)
+
+
+class LinearTF32Function(torch.autograd.Function):
+    """``act(x @ weight.T + bias) + residual`` with the forward on the tcgen05
+    kernel (``fbbev_linear_fwd``: same 3xTF32 arithmetic as inference) and the
+    backward as plain library GEMMs::
+
+        g  = grad * (y > 0)           (ReLU only)
+        dx = g @ weight    dW = g^T @ x    db = sum_rows(g)    dresidual = grad
+
+    The reference trains these layers through cuBLAS in both directions
+    (nn.Linear); here only the backward is a library call.  LayerNorm stays a
+    torch op on this route (its backward needs the row statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, residual):
+        assert not (relu and residual is not None)
+        y = linear_fused(
+            x.detach(), weight.detach(),
+            None if bias is None else bias.detach(), relu=relu,
+            residual=None if residual is None else residual.detach())
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight, y = ctx.saved_tensors
+        g = grad * (y > 0).to(grad.dtype) if ctx.relu else grad
+        n, k = weight.shape
+        g2 = g.reshape(-1, n)
+        gx = gw = gb = gr = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x.reshape(-1, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        if ctx.has_res and ctx.needs_input_grad[4]:
+            gr = grad
+        return gx, gw, gb, None, gr
+
+
+def linear_train(x, weight, bias=None, relu=False, residual=None):
+    """Differentiable ``act(x @ weight.T + bias) + residual``; forward on the
+    tensor-core kernel.  Shapes the kernel does not take (k or n not a multiple
+    of 4) must be handled by the caller."""
+    if relu and residual is not None:
+        return LinearTF32Function.apply(x, weight, bias, True, None) + residual
+    return LinearTF32Function.apply(x, weight, bias, relu, residual)

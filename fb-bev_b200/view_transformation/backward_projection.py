@@ -82,11 +82,16 @@ def _const_tensor(values, device):
 
 
 def _fused_linear_on(x, *dropouts):
-    """The tensor-core Linear path: CUDA fp32 input, no autograd, no active
-    dropout."""
+    """The tensor-core Linear path: CUDA fp32 input, no active dropout.  With
+    autograd recording the forward stays on the tcgen05 kernel
+    (``ops.linear.LinearTF32Function``; backward = library GEMMs) unless
+    ``FBBEV_TRAIN_TORCH_LINEAR=1`` asks for nn.Linear end to end."""
     if os.environ.get('FBBEV_TORCH_LINEAR', '0') == '1':
         return False
-    if torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32:
+    if torch.is_grad_enabled() and \
+            os.environ.get('FBBEV_TRAIN_TORCH_LINEAR', '0') == '1':
+        return False
+    if not x.is_cuda or x.dtype != torch.float32:
         return False
     for d in dropouts:
         if isinstance(d, nn.Dropout) and d.training and d.p > 0:
@@ -102,6 +107,12 @@ def _linear(mod, x, relu=False, residual=None, norm=None):
         y = mod(x)
         y = F.relu(y) if relu else y
         y = y + residual if residual is not None else y
+        return norm(y) if norm is not None else y
+    if torch.is_grad_enabled():
+        # training: forward on the same kernel, differentiable; LayerNorm as a
+        # torch op (its backward needs the row statistics)
+        y = _linear_ops.linear_train(x, mod.weight, mod.bias, relu=relu,
+                                     residual=residual)
         return norm(y) if norm is not None else y
     if norm is not None and not _linear_ops.ln_supported(n):
         # rows wider than the LayerNorm epilogue keeps in shared memory
@@ -122,7 +133,8 @@ def _linear_pair(owner, mod_a, mod_b, x, x_add=None):
     input, one launch when their widths allow (the addition happens in the
     kernel's loader); set ``FBBEV_LINEAR_PAIR=0`` for two launches."""
     if (os.environ.get('FBBEV_LINEAR_PAIR', '1') == '1'
-            and mod_a.weight.shape[1] % 4 == 0):
+            and mod_a.weight.shape[1] % 4 == 0
+            and not torch.is_grad_enabled()):
         return _linear_ops.linear_pair(
             x, mod_a.weight, mod_a.bias, mod_b.weight, mod_b.bias,
             owner.__dict__.setdefault('_pair_cache', {}), x_add=x_add)
