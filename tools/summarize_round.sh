@@ -1,7 +1,7 @@
 # After tools/profile_round.sh: turn gpurun_out/ captures into the tracked summaries under profiles/.
 R=${1:-r02}
 python tools/summarize_ncu.py launches gpurun_out/${R}_launches.csv profiles/${R}_launches.md
-for k in dense_write_kernel interval_sums_kernel linear_tf32_kernel da_sca_smem_kernel msda_fused_fwd_kernel history_warp_kernel; do
+for k in dense_write_kernel interval_sums_kernel linear_tf32_kernel ffn_tf32_kernel da_sca_smem_kernel msda_fused_fwd_kernel history_warp_kernel; do
   [ -f gpurun_out/${R}_$k.ncu-rep ] && python tools/summarize_ncu.py kernel gpurun_out/${R}_$k.ncu-rep profiles/${R}_$k.json
 done
 python - <<PY
@@ -19,5 +19,6 @@ except Exception as e:
     print("traffic summary skipped:", e)
 PY
 cp gpurun_out/${R}_bench.json profiles/${R}_bench_line.json 2>/dev/null
+for c in unit frames16 bwd_only large; do [ -s gpurun_out/${R}_bench_$c.json ] && cp gpurun_out/${R}_bench_$c.json profiles/${R}_bench_$c.json; done
 cp gpurun_out/${R}_clocks.csv profiles/${R}_clocks.csv 2>/dev/null
 ls -la profiles/
