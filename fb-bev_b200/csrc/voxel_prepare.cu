@@ -64,7 +64,7 @@ __device__ __forceinline__ void voxelize_point(float x, float y, float z,
                      __ldg(g.depth_prob + p) > g.depth_thresh);
   int r = -1;
   if (keep) {
-    const int64_t b = p / per_b;
+    const int64_t b = (unsigned)p / (unsigned)per_b;   // p, per_b < 2^31
     r = (int)(((b * g.gz + cz) * g.gy + cy) * g.gx + cx);
     atomicAdd(hist + r, 1);
   }
@@ -108,13 +108,15 @@ __global__ void __launch_bounds__(kPrepThreads) prep_voxelize_cams_kernel(
     int* __restrict__ rank, int* __restrict__ hist) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pts) return;
-  const int w = (int)(p % cg.W);
-  int64_t t = p / cg.W;
-  const int h = (int)(t % cg.H);
-  t /= cg.H;
-  const int d = (int)(t % cg.D);
-  const int64_t bn = t / cg.D;
-  const int64_t b = bn / cg.N;
+  // n_pts < 2^31 (checked by the entry point): 32-bit divisions
+  const unsigned pu = (unsigned)p;
+  const int w = (int)(pu % (unsigned)cg.W);
+  unsigned t = pu / (unsigned)cg.W;
+  const int h = (int)(t % (unsigned)cg.H);
+  t /= (unsigned)cg.H;
+  const int d = (int)(t % (unsigned)cg.D);
+  const int64_t bn = t / (unsigned)cg.D;
+  const int64_t b = (unsigned)bn / (unsigned)cg.N;
   const float* pt = cg.ptr + bn * 3;
   float x = __fsub_rn(__ldg(cg.us + w), __ldg(pt + 0));
   float y = __fsub_rn(__ldg(cg.vs + h), __ldg(pt + 1));
@@ -239,15 +241,24 @@ __global__ void __launch_bounds__(kPrepThreads) prep_scan_apply_kernel(
   int run_pts = bs.x + v.x - mine.x;  // exclusive prefix for this thread
   int run_int = bs.y + v.y - mine.y;
   const bool planned = plan.tile_first != nullptr;
+  // sample / in-sample voxel of the thread's first item: ONE 64-bit division
+  // per thread, then counted along (the tile size is a power of two); the
+  // per-item divisions cost 11 us of a 43 us index build
+  int64_t pb = 0, plocal = 0;
+  if (planned && base < n_vox) {
+    pb = base / plan.zyx;
+    plocal = base - pb * plan.zyx;
+  }
+  const int t_mask = plan.T - 1, t_shift = 31 - __clz(plan.T);
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const int64_t i = base + k;
     if (i < n_vox) {
       offset[i] = run_pts;
       if (planned) {
-        const int64_t b = i / plan.zyx, local = i - b * plan.zyx;
-        if (local % plan.T == 0)
-          plan.tile_first[b * plan.tiles_per_b + local / plan.T] = run_int;
+        if (((int)plocal & t_mask) == 0)
+          plan.tile_first[pb * plan.tiles_per_b + (plocal >> t_shift)] = run_int;
+        if (++plocal == plan.zyx) { plocal = 0; ++pb; }
       }
       if (h[k] > 0) {
         interval_starts[run_int] = run_pts;   // view_transformer.py:597
@@ -316,8 +327,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_order_kernel(
   ranks_bev[dst] = r;
   ranks_depth[dst] = p;  // arange(num_points), view_transformer.py:561-562
   // arange(num_points // D).reshape(B,N,1,H,W).expand(B,N,D,H,W), :563-568
-  const int64_t bn = p / ((int64_t)D * hw);
-  ranks_feat[dst] = (int)(bn * hw + p % hw);
+  const unsigned bn = (unsigned)p / (unsigned)(D * hw);   // D * hw <= n_pts < 2^31
+  ranks_feat[dst] = (int)(bn * (unsigned)hw + (unsigned)p % (unsigned)hw);
 }
 
 struct PrepWorkspace {
