@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
     const int* __restrict__ tile_first, const int* __restrict__ seg_rank,
     const int* __restrict__ interval_starts,
     const int* __restrict__ interval_lengths, int c, int zyx,
-    const float* __restrict__ add, int yx_n, float* __restrict__ out) {
+    const float* __restrict__ add, int yx_n, float* __restrict__ out, int part) {
+  // `part`: 0 every tile; 1 only the EMPTY tiles (their zero / `add` stream
+  // needs nothing but the plan, so it can run beside the interval sums); 2 only
+  // the tiles that hold intervals.
   // `add` (may be null): a (B, C, Y*X) map added to every Z slice while the
   // tile streams out -- FBOCC's `bev_feat_refined[..., None] + bev_feat`
   // (fbocc.py:365-366) without a second pass over the volume
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(2 * T, 1280 / (2 * T)) dense_write_kernel(
   const int i0 = __ldg(tile_first + tile);
   const int i1 = __ldg(tile_first + tile + 1);
   const int nrows = min(i1 - i0, T);
+  if ((part == 1 && nrows > 0) || (part == 2 && nrows <= 0)) return;
   const int c4 = c >> 2;
   constexpr int LPR = T / 4;        // lanes per channel row
   constexpr int RPW = kWarp / LPR;  // rows per warp instruction
@@ -575,7 +579,7 @@ template <int T>
 static int launch_write(const SplitWs& w, const int* interval_starts,
                         const int* interval_lengths, int c, int64_t zyx,
                         int tiles_per_b, int batch, const float* add, int yx_n,
-                        float* out, cudaStream_t st) {
+                        float* out, cudaStream_t st, int part = 0) {
   const size_t smem = write_smem_bytes(T, c);
   auto k = dense_write_kernel<T>;
   if (smem > 48 * 1024) {
@@ -585,8 +589,49 @@ static int launch_write(const SplitWs& w, const int* interval_starts,
   }
   k<<<dim3((unsigned)tiles_per_b, (unsigned)batch), 2 * T, smem, st>>>(
       w.V, w.X, w.tile_first, w.seg_rank, interval_starts, interval_lengths, c,
-      (int)zyx, add, yx_n, out);
+      (int)zyx, add, yx_n, out, part);
   return launch_status();
+}
+
+static int launch_write_any(int T, const SplitWs& w, const int* interval_starts,
+                            const int* interval_lengths, int c, int64_t zyx,
+                            int tiles_per_b, int batch, const float* add,
+                            int yx_n, float* out, cudaStream_t st, int part) {
+  switch (T) {
+    case 128:
+      return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
+                               tiles_per_b, batch, add, yx_n, out, st, part);
+    case 64:
+      return launch_write<64>(w, interval_starts, interval_lengths, c, zyx,
+                              tiles_per_b, batch, add, yx_n, out, st, part);
+    default:
+      return launch_write<32>(w, interval_starts, interval_lengths, c, zyx,
+                              tiles_per_b, batch, add, yx_n, out, st, part);
+  }
+}
+
+// Side stream for the zero stream of the empty tiles (one per host thread,
+// created on first use -- warm up once before capturing a CUDA graph).
+struct PoolSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static PoolSide* pool_side() {
+  static thread_local PoolSide s;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (s.stream && s.device == dev) return &s;
+  if (s.stream) return nullptr;   // another device on this thread: no overlap
+  if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+    s.stream = nullptr;
+    cudaGetLastError();
+    return nullptr;
+  }
+  s.device = dev;
+  return &s;
 }
 
 int split_launch(const float* depth, const float* feat, const int* ranks_depth,
@@ -606,6 +651,23 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
       split_layout(workspace, batch, zyx, n_intervals_max, n_points_max, c);
   const int T = split_pick_tile(c);
   const int tiles_per_b = (int)ceil_div64(zyx, T);
+  // One-shot op (sums + write): the empty tiles' zero stream -- 79 % of the
+  // 200x200x16 volume -- depends on the plan only, so it is launched on a side
+  // stream beside the interval sums (latency-bound, 18 us, few bytes) and the
+  // tiles that hold intervals follow the sums (FBBEV_POOL_OVERLAP=0: serial).
+  static const bool overlap_on = [] {
+    const char* e = getenv("FBBEV_POOL_OVERLAP");
+    return !(e && e[0] == '0');
+  }();
+  PoolSide* side = (do_sums && do_write && n_intervals_max > 0 && overlap_on)
+                       ? pool_side() : nullptr;
+  if (side) {
+    if (cudaEventRecord(side->fork, st) != cudaSuccess ||
+        cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+      cudaGetLastError();
+      side = nullptr;
+    }
+  }
   if (do_sums && n_intervals_max > 0) {
     count_launch();
     const unsigned grid = (unsigned)w.n_sum_ctas;
@@ -627,19 +689,22 @@ int split_launch(const float* depth, const float* feat, const int* ranks_depth,
     int rc = launch_status();
     if (rc) return rc;
   }
+  if (side) {   // after the sums: their CTAs take their SM slots first
+    count_launch();
+    int rc = launch_write_any(T, w, interval_starts, interval_lengths, c, zyx,
+                              tiles_per_b, batch, add, yx_n, out, side->stream, 1);
+    if (rc) return rc;
+  }
   if (!do_write) return FBBEV_OK;
   count_launch();
-  switch (T) {
-    case 128:
-      return launch_write<128>(w, interval_starts, interval_lengths, c, zyx,
-                               tiles_per_b, batch, add, yx_n, out, st);
-    case 64:
-      return launch_write<64>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, batch, add, yx_n, out, st);
-    default:
-      return launch_write<32>(w, interval_starts, interval_lengths, c, zyx,
-                              tiles_per_b, batch, add, yx_n, out, st);
+  int rc = launch_write_any(T, w, interval_starts, interval_lengths, c, zyx,
+                            tiles_per_b, batch, add, yx_n, out, st, side ? 2 : 0);
+  if (side) {
+    if (cudaEventRecord(side->join, side->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
+      return (int)cudaGetLastError();
   }
+  return rc;
 }
 
 int split_zmean(const int* interval_starts, const int* interval_lengths,

@@ -82,6 +82,14 @@ int fbbev_bev_pool_v2_fwd(const float* depth, const float* feat,
  *   upper bound of the kept points when the buffers are over-allocated).
  * n_voxels_per_sample = Z*Y*X.  Requires B*Z*Y*X < 2^31 (int32 ranks).
  * workspace: >= fbbev_bev_pool_v2_dense_workspace_bytes(...) bytes.
+ * Scheduling (the one exception to "all work goes to `stream`"): the zero
+ * stream of the EMPTY voxel tiles depends on the plan only and is enqueued on a
+ * library-owned side stream (one per host thread, created on first use) that
+ * forks from and joins back into `stream` with events inside the call, so it
+ * runs beside the interval sums; the caller sees ordinary stream semantics (the
+ * call is complete on `stream` when everything is).  Warm up once before
+ * capturing a CUDA graph.  FBBEV_POOL_OVERLAP=0 in the environment keeps
+ * everything on `stream`.
  */
 size_t fbbev_bev_pool_v2_dense_workspace_bytes(int32_t batch,
                                                int64_t n_voxels_per_sample,
