@@ -121,3 +121,36 @@ def test_token_major_positional_encoding_cache():
         root.mul_(2.0)                                         # version bump
         c = enc._token_major(root.flatten(2).permute(2, 0, 1).permute(1, 0, 2))
         assert c is not a and torch.equal(c, view)
+
+
+def test_linear_train_backward_formulas(monkeypatch):
+    """ops.linear.LinearTF32Function: the three gradient products of the
+    training route (dx = g W, dW = g^T x, db = sum g, dresidual = g, ReLU mask
+    from the saved output) against autograd, with the tcgen05 forward replaced
+    by its definition so that the check runs on the CPU in float64."""
+    import torch.nn.functional as F
+    from fbbev_b200.ops import linear as lin
+
+    def forward_definition(x, weight, bias=None, relu=False, residual=None,
+                           **kw):
+        y = F.linear(x, weight, bias)
+        y = y.relu() if relu else y
+        return y if residual is None else y + residual
+    monkeypatch.setattr(lin, "linear_fused", forward_definition)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 7, 8, generator=g, dtype=torch.float64,
+                    requires_grad=True)
+    w = torch.randn(12, 8, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(12, generator=g, dtype=torch.float64, requires_grad=True)
+    r = torch.randn(5, 7, 12, generator=g, dtype=torch.float64,
+                    requires_grad=True)
+    assert torch.autograd.gradcheck(
+        lambda x, w, b: lin.linear_train(x, w, b, relu=True), (x, w, b))
+    assert torch.autograd.gradcheck(
+        lambda x, w, b, r: lin.linear_train(x, w, b, residual=r), (x, w, b, r))
+    assert torch.autograd.gradcheck(
+        lambda x, w: lin.linear_train(x, w, None), (x, w))
+    # relu + residual composes (the kernel is never asked for both)
+    assert torch.autograd.gradcheck(
+        lambda x, w, b, r: lin.linear_train(x, w, b, relu=True, residual=r),
+        (x, w, b, r))
